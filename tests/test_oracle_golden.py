@@ -1,0 +1,161 @@
+"""The numpy restatement (oracle/nts_oracle.py) against the golden vectors dumped by the UNMODIFIED
+reference CPU operators (tests/golden/*.npz, produced by oracle/make_golden.py at P = 1, 2, 4, 8).
+Integer artefacts must be bit-exact; float results within 2e-6 relative of the reference's own
+CPU result (same summation order, FMA contraction is the only freedom)."""
+import numpy as np
+
+import nts_oracle as O
+
+RTOL = 2e-6
+ATOL = 2e-6
+
+
+def close(a, b):
+    np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL)
+
+
+def rows_as_multisets(offsets, idx):
+    out = idx.copy()
+    off = offsets.astype(np.int64)
+    for r in range(off.shape[0] - 1):
+        out[off[r]:off[r + 1]] = np.sort(out[off[r]:off[r + 1]])
+    return out
+
+
+def test_degrees_and_partition(golden):
+    g = golden
+    out_deg, in_deg = O.degrees(g.edges, g.V)
+    assert np.array_equal(out_deg, g.get(0, "out_degree"))
+    assert np.array_equal(in_deg, g.get(0, "in_degree"))
+    po = O.partition_offsets(g.edges, g.V, g.P)
+    assert np.array_equal(po, g.partition_offset)
+
+
+def test_chunks_bit_exact(golden):
+    g = golden
+    po = g.partition_offset
+    for r in range(g.P):
+        chunks = O.build_chunks(g.edges, g.V, po, r)
+        mirrors = O.has_mirror_at(g.edges, g.V, po, r)
+        for i, c in enumerate(chunks):
+            t = "chunk%d_" % i
+            meta = g.get(r, t + "meta")
+            assert meta[0] == c.edge_size
+            assert (meta[3], meta[4]) == c.src_range and (meta[5], meta[6]) == c.dst_range
+            assert np.array_equal(c.column_offset, g.get(r, t + "column_offset"))
+            assert np.array_equal(c.row_indices, g.get(r, t + "row_indices"))
+            # weights: bit-exact float32
+            assert np.array_equal(c.edge_weight_forward.view(np.uint32),
+                                  g.get(r, t + "edge_weight_forward").view(np.uint32))
+            assert np.array_equal(c.row_offset, g.get(r, t + "row_offset"))
+            # CSR rows: the reference's order inside a source row is a race; compare as multisets
+            ref_ci = g.get(r, t + "column_indices")
+            assert np.array_equal(rows_as_multisets(c.row_offset, c.column_indices),
+                                  rows_as_multisets(c.row_offset, ref_ci))
+            # backward weights follow the reference's own CSR order
+            ro = c.row_offset.astype(np.int64)
+            src_of_edge = np.repeat(np.arange(ro.shape[0] - 1), np.diff(ro)) + c.src_range[0]
+            out_deg, in_deg = O.degrees(g.edges, g.V)
+            w_ref_order = O.weights_norm_degree(src_of_edge, ref_ci.astype(np.int64), out_deg, in_deg)
+            assert np.array_equal(w_ref_order.view(np.uint32),
+                                  g.get(r, t + "edge_weight_backward").view(np.uint32))
+            assert np.array_equal(c.source_active, g.get(r, t + "source_active"))
+            assert np.array_equal(mirrors[i], g.get(r, t + "has_mirror_at"))
+
+
+def test_csc_segment_is_in_degree(golden):
+    """test/testcsr.cpp:40-44 - in-degree == CSC segment length (summed over a rank's chunks)."""
+    g = golden
+    po = g.partition_offset
+    in_deg_raw = np.bincount(g.edges[:, 1], minlength=g.V)
+    for r in range(g.P):
+        chunks = O.build_chunks(g.edges, g.V, po, r)
+        seg = sum(np.diff(c.column_offset.astype(np.int64)) for c in chunks)
+        assert np.array_equal(seg, in_deg_raw[int(po[r]):int(po[r + 1])])
+
+
+def test_mirror_index_and_whole_topo(golden):
+    g = golden
+    po = g.partition_offset
+    for r in range(g.P):
+        mi, M = O.mirror_index(g.edges, g.V, po, r)
+        assert np.array_equal(mi, g.get(r, "mirror_index"))
+        assert M == int(g.get(r, "meta")[6])
+        co, ri, cro, ci = O.whole_graph_topo(g.edges, g.V, po, r)
+        assert np.array_equal(co, g.get(r, "whole_column_offset"))
+        assert np.array_equal(ri, g.get(r, "whole_row_indices"))
+        assert np.array_equal(cro, g.get(r, "whole_compressed_row_offset"))
+        assert np.array_equal(rows_as_multisets(cro, ci),
+                              rows_as_multisets(cro, g.get(r, "whole_column_indices")))
+
+
+def _global(g, key):
+    return np.concatenate([g.mat(r, key) for r in range(g.P)], axis=0)
+
+
+def test_gcn_forward_backward(golden):
+    g = golden
+    X = _global(g, "X")
+    G = _global(g, "G")
+    close(O.gcn_forward_all(g.edges, g.V, g.P, X), _global(g, "gcn_Y"))
+    close(O.gcn_backward_all(g.edges, g.V, g.P, G), _global(g, "gcn_dX"))
+
+
+def test_partition_invariance(golden):
+    """SURVEY 8c tier (1): the P-rank result equals the single-rank result."""
+    g = golden
+    X = _global(g, "X")
+    close(O.gcn_forward_all(g.edges, g.V, 1, X), _global(g, "gcn_Y"))
+
+
+def test_edge_ops(golden):
+    g = golden
+    po = g.partition_offset
+    Xg = _global(g, "X")
+    for r in range(g.P):
+        Vp, Ep, M = (int(x) for x in g.get(r, "meta")[4:7])
+        co = g.get(r, "whole_column_offset")
+        ri = g.get(r, "whole_row_indices")
+        mi = g.get(r, "mirror_index")
+        mirror = O.get_dep_neighbor(g.edges, g.V, po, r, Xg)
+        close(mirror, g.mat(r, "dep_mirror"))
+        Ge = g.mat(r, "Ge")
+        Xl = g.mat(r, "X")
+        Gl = g.mat(r, "G")
+        if g.has(r, "scatter_src_msg"):
+            assert np.array_equal(O.scatter_src_mirror_to_msg(co, ri, mi, mirror), g.mat(r, "scatter_src_msg"))
+            assert np.array_equal(O.scatter_dst_to_msg(co, Xl), g.mat(r, "scatter_dst_msg"))
+            assert np.array_equal(O.scatter_dst_to_msg(co, Gl), g.mat(r, "aggregate_dst_dmsg"))
+        close(O.gather_msg_to_src_mirror(co, ri, mi, Ge, M), g.mat(r, "scatter_src_dmirror"))
+        close(O.gather_msg_to_dst(co, Ge), g.mat(r, "scatter_dst_dX"))
+        close(O.gather_msg_to_dst(co, Ge), g.mat(r, "aggregate_dst_Y"))
+        a = O.edge_softmax_forward(co, g.mat(r, "softmax_in", 1))
+        close(a, g.mat(r, "softmax_out", 1))
+        close(O.edge_softmax_backward(co, g.mat(r, "softmax_out", 1), g.mat(r, "softmax_gout", 1)),
+              g.mat(r, "softmax_gin", 1))
+        att = g.mat(r, "softmax_out", 1)
+        close(O.aggregate_dst_fuse_weight_forward(co, ri, mi, mirror, att), g.mat(r, "fuse_Y"))
+        dm, dw = O.aggregate_dst_fuse_weight_backward(co, ri, mi, mirror, att, Gl, M,
+                                                      reference_double_count=True)
+        # The reference's backward is racy here: OMP threads `nts_comp` (non-atomic) into shared mirror
+        # rows (core/ntsDistCPUGraphOp.hpp:572-578), so a few elements of its own dump have lost
+        # updates.  Require >= 99% of the elements to agree; the rest are the reference's race.
+        ref_dm = g.mat(r, "fuse_dmirror")
+        ok = np.isclose(dm, ref_dm, rtol=2e-5, atol=2e-5)
+        assert ok.size == 0 or ok.mean() >= 0.99, ok.mean()
+        close(dw, g.mat(r, "fuse_dweight", 1))
+
+
+def test_dep_neighbor_backward(golden):
+    """DistGetDepNbrOp::backward: every rank returns its mirror gradients to the owners, who sum them."""
+    g = golden
+    po = g.partition_offset
+    F = g.F
+    acc = np.zeros((g.V, F), dtype=np.float32)
+    for r in range(g.P):
+        mi = g.get(r, "mirror_index")
+        srcs = np.nonzero(mi[1:] != mi[:-1])[0]
+        Gm = g.mat(r, "dep_Gm")
+        np.add.at(acc, srcs, Gm[mi[srcs].astype(np.int64)])
+    ref = np.concatenate([g.mat(r, "dep_dX") for r in range(g.P)], axis=0)
+    np.testing.assert_allclose(acc, ref, rtol=1e-5, atol=1e-5)
