@@ -1,0 +1,220 @@
+/* nts_b200.h - C ABI of libnts_b200.so: NeutronStar's sparse neighbour-aggregation hot path,
+ * hand-written for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  Every entry point replaces one member of the reference's device
+ * interface `cuda/ntsCUDA.hpp` (free functions :25-47, `deviceCSC` :49-95, `Cuda_Stream` :97-217,
+ * implemented by `cuda/ntsCUDAGraphOP.cu`); the reference interface it stands in for is cited at
+ * each declaration.  The C++ surface of that header (class `Cuda_Stream`, ...) is provided on top
+ * of this ABI by `include/nts_cuda_compat.hpp` so the reference's host code links unchanged - see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes; all device pointers are CUDA device (or mapped/peer) addresses,
+ *    `stream` is a `cudaStream_t` passed as `void*` (NULL = the legacy default stream);
+ *  - feature matrices are row-major contiguous float32 [rows, feature_size], borrowed, never
+ *    re-laid-out (the reference borrows torch storage the same way, core/NtsScheduler.hpp:505-515);
+ *  - vertex ids / offsets are uint32 (`VertexId_CUDA`, cuda/cuda_type.h:21); all address
+ *    arithmetic is 64-bit (the reference's 32-bit `feature_size*batch_size` products overflow for
+ *    V*F >= 2^32, cuda/ntsCUDAFuseKernel.cuh:280,299);
+ *  - aggregation kernels ACCUMULATE into `output` (caller zeroes), exactly like the reference
+ *    (cuda/ntsCUDAFuseKernel.cuh:272-309; tensors come zero-filled from NtsScheduler::NewKeyTensor);
+ *  - every call is asynchronous on `stream` unless stated; launch errors are checked;
+ *  - return value: 0 on success, otherwise the cudaError_t (or -1 for argument errors).  The
+ *    message is available from nts_last_error().  With NTS_B200_ABORT_ON_ERROR=1 in the
+ *    environment the library prints the message and exit(1)s instead - the reference's convention
+ *    (cuda/ntsCUDAGraphOP.cu:13-19).
+ *  - there is no CPU fallback anywhere in this library.
+ */
+#ifndef NTS_B200_H
+#define NTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint32_t nts_vid_t; /* VertexId_CUDA, cuda/cuda_type.h:21 */
+
+/* ---- library / device ----------------------------------------------------------------------- */
+int nts_version(void);                 /* ABI version, currently 1 */
+const char *nts_last_error(void);      /* thread-local text of the last failure */
+int nts_device_count(void);
+int nts_set_device(int device);        /* the reference never calls cudaSetDevice (always device 0) */
+int nts_device_sm_count(int *sm_count);
+int nts_device_synchronize(void);      /* ::CUDA_DEVICE_SYNCHRONIZE(), ntsCUDA.hpp:46 */
+int nts_device_reset(void);            /* ::ResetDevice(), ntsCUDA.hpp:47 */
+
+/* ---- memory (ntsCUDA.hpp:25-45) ---------------------------------------------------------------- */
+void *nts_malloc_device(size_t bytes);            /* ::cudaMallocGPU / allocate_gpu_buffer / allocate_gpu_edge */
+int nts_free_device(void *ptr);                   /* ::FreeBuffer / ::FreeEdge */
+void *nts_malloc_pinned(size_t bytes);            /* ::cudaMallocPinned (cudaHostAllocMapped) */
+int nts_free_pinned(void *ptr);                   /* ::ntsFreeHost */
+void *nts_pinned_device_pointer(void *host_ptr);  /* ::getDevicePointer */
+int nts_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes, void *stream, int sync);
+                                                  /* ::move_data_in / move_edge_in / move_bytes_in */
+int nts_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes, void *stream, int sync);
+                                                  /* ::move_result_out */
+int nts_memcpy_d2d(void *dst_device, const void *src_device, size_t bytes, void *stream);
+int nts_zero(void *device_ptr, size_t bytes, void *stream); /* ::zero_buffer */
+
+/* ---- streams / events (Cuda_Stream ctor, destory_Stream, CUDA_DEVICE_SYNCHRONIZE; ntsCUDA.hpp:97-103) */
+void *nts_stream_create(int non_blocking);
+int nts_stream_destroy(void *stream);
+int nts_stream_synchronize(void *stream);
+void *nts_event_create(int with_timing);
+int nts_event_destroy(void *event);
+int nts_event_record(void *event, void *stream);
+int nts_stream_wait_event(void *stream, void *event);
+int nts_event_elapsed_ms(void *start, void *stop, float *ms);
+
+/* ---- the hot path: segmented weighted gather-sum (SpMM-like) --------------------------------------
+ * output[r, :] += sum_{e in [offsets[r], offsets[r+1])} input[indices[e] - index_base, :] * (weight ? weight[e] : 1)
+ *
+ * Forward  = Cuda_Stream::Gather_By_Dst_From_Src[_Optim] (ntsCUDA.hpp:125-138, ntsCUDAGraphOP.cu:157-211):
+ *            offsets = column_offset[Vdst+1], indices = row_indices (GLOBAL source ids), index_base = src_start.
+ * Backward = Cuda_Stream::Gather_By_Src_From_Dst[_Optim] (ntsCUDA.hpp:139-152, ntsCUDAGraphOP.cu:213-281):
+ *            offsets = row_offset[Vsrc+1], indices = column_indices (GLOBAL destination ids), index_base = dst_start.
+ * The two named wrappers keep the reference's parameter list (minus the unused tensor_weight flag).
+ */
+int nts_segment_gather_sum(const float *input, float *output, const float *weight,
+                           const nts_vid_t *indices, const nts_vid_t *offsets, nts_vid_t index_base,
+                           nts_vid_t n_rows, uint64_t n_edges, nts_vid_t feature_size, void *stream);
+
+int nts_gather_by_dst_from_src(const float *input, float *output, const float *weight_forward,
+                               const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                               nts_vid_t src_start, nts_vid_t src_end, nts_vid_t dst_start,
+                               nts_vid_t dst_end, nts_vid_t edges, nts_vid_t batch_size,
+                               nts_vid_t feature_size, int with_weight, void *stream);
+
+int nts_gather_by_src_from_dst(const float *input, float *output, const float *weight_backward,
+                               const nts_vid_t *row_offset, const nts_vid_t *column_indices,
+                               nts_vid_t src_start, nts_vid_t src_end, nts_vid_t dst_start,
+                               nts_vid_t dst_end, nts_vid_t edges, nts_vid_t batch_size,
+                               nts_vid_t feature_size, int with_weight, void *stream);
+
+/* Same contraction with the source row taken through a slot table instead of `index - base`:
+ * row = slot_of[indices[e]].  Used with MirrorIndex (core/PartitionedGraph.hpp:295-305) for the fused
+ * GAT aggregation, DistAggregateDstFuseWeight::forward (core/ntsDistCPUGraphOp.hpp:516-546), and with
+ * the compact receive-staging slots of the multi-GPU exchange. */
+int nts_segment_gather_sum_slots(const float *input, float *output, const float *weight,
+                                 const nts_vid_t *indices, const nts_vid_t *offsets,
+                                 const nts_vid_t *slot_of, nts_vid_t n_rows, uint64_t n_edges,
+                                 nts_vid_t feature_size, void *stream);
+
+/* Tuning / introspection of the aggregation kernel (does not change results beyond fp32
+ * re-association): variant 0 = auto, see DESIGN.md "kernel variants". */
+int nts_aggregate_set_variant(int variant, int edges_per_warp);
+int nts_aggregate_last_launch(int *grid, int *block, int *smem_bytes, int *variant);
+uint64_t nts_kernel_launch_count(void); /* kernels launched by this library since load */
+
+/* ---- edge-granular operators (GAT building blocks) -------------------------------------------------
+ * All take the whole-partition CSC of core/PartitionedGraph.hpp:105-143 (column_offset[Vp+1], row_indices[Ep]
+ * global source ids) as uploaded by `deviceCSC` (ntsCUDA.hpp:49-95). `batch_size` = Vp. */
+/* msg[e,:] = mirror[mirror_index[row_indices[e]],:]      Cuda_Stream::Scatter_Src_Mirror_to_Msg (ntsCUDA.hpp:154) */
+int nts_scatter_src_mirror_to_msg(float *message, const float *src_mirror_feature,
+                                  const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                  const nts_vid_t *mirror_index, nts_vid_t batch_size,
+                                  nts_vid_t feature_size, void *stream);
+/* mirror_grad[mirror_index[row_indices[e]],:] += msg[e,:]  Cuda_Stream::Gather_Msg_To_Src_Mirror (ntsCUDA.hpp:159) */
+int nts_gather_msg_to_src_mirror(float *src_mirror_feature, const float *message,
+                                 const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                 const nts_vid_t *mirror_index, nts_vid_t batch_size,
+                                 nts_vid_t feature_size, void *stream);
+/* msg[e,:] = dst_feature[dst(e),:]                         Cuda_Stream::Scatter_Dst_to_Msg (ntsCUDA.hpp:164) */
+int nts_scatter_dst_to_msg(float *message, const float *dst_feature, const nts_vid_t *row_indices,
+                           const nts_vid_t *column_offset, nts_vid_t batch_size,
+                           nts_vid_t feature_size, void *stream);
+/* dst_feature[d,:] += sum_{e->d} msg[e,:]                  Cuda_Stream::Gather_Msg_to_Dst (ntsCUDA.hpp:168) */
+int nts_gather_msg_to_dst(float *dst_feature, const float *message, const nts_vid_t *row_indices,
+                          const nts_vid_t *column_offset, nts_vid_t batch_size,
+                          nts_vid_t feature_size, void *stream);
+/* a[seg,h] = softmax_seg(m[seg,h]) per destination segment and column h (max-subtracted; oracle =
+ * DistEdgeSoftMax::forward core/ntsDistCPUGraphOp.hpp:449-470); msg_cached receives a copy.
+ * Cuda_Stream::Edge_Softmax_Forward_Block (ntsCUDA.hpp:172) - the reference kernel handles 1 column only. */
+int nts_edge_softmax_forward(float *msg_output, const float *msg_input, float *msg_cached,
+                             const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                             nts_vid_t batch_size, nts_vid_t feature_size, void *stream);
+/* g_in[e,h] = a[e,h]*g[e,h] - a[e,h]*sum_seg(g*a)            Cuda_Stream::Edge_Softmax_Backward_Block (ntsCUDA.hpp:177) */
+int nts_edge_softmax_backward(float *msg_input_grad, const float *msg_output_grad,
+                              const float *msg_cached, const nts_vid_t *row_indices,
+                              const nts_vid_t *column_offset, nts_vid_t batch_size,
+                              nts_vid_t feature_size, void *stream);
+/* message_grad[e,:] += input[dst(e),:]                     Cuda_Stream::Scatter_Grad_Back_To_Message (ntsCUDA.hpp:194) */
+int nts_scatter_grad_back_to_message(const float *input, float *message_grad,
+                                     const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                     nts_vid_t batch_size, nts_vid_t feature_size, void *stream);
+
+/* Fused GAT aggregation backward, DistAggregateDstFuseWeight::backward (core/ntsDistCPUGraphOp.hpp:548-589)
+ * WITHOUT the reference's spurious extra unweighted add (:572):
+ *   mirror_grad[slot(e),:] += a[e] * g[dst(e),:]        (needs mirror_grad zeroed by the caller)
+ *   a_grad[e]               = < mirror[slot(e),:], g[dst(e),:] >  */
+int nts_aggregate_dst_fuse_weight_backward(float *mirror_grad, float *edge_weight_grad,
+                                           const float *mirror, const float *edge_weight,
+                                           const float *dst_grad, const nts_vid_t *row_indices,
+                                           const nts_vid_t *column_offset,
+                                           const nts_vid_t *mirror_index, nts_vid_t batch_size,
+                                           nts_vid_t feature_size, void *stream);
+
+/* ---- (vid,row) message records: the reference's host-staged exchange format (comm/network.h:143-149) ---
+ * record k = { uint32 vid; float row[feature_size]; }, read through mapped pinned host memory. */
+/* mirror[vid - partition_start,:] = record.row if vid in [partition_start, partition_end)
+ * Cuda_Stream::deSerializeToGPU (ntsCUDA.hpp:113, ntsCUDATransferKernel.cuh:70-93) */
+int nts_deserialize_records(float *mirror, const float *records, nts_vid_t n_records,
+                            nts_vid_t feature_size, nts_vid_t partition_start,
+                            nts_vid_t partition_end, void *stream);
+/* Y[vid - partition_start,:] += record.row
+ * Cuda_Stream::aggregate_comm_result_debug (ntsCUDA.hpp:117, ntsCUDATransferKernel.cuh:49-68) */
+int nts_aggregate_records(float *aggregate, const float *records, nts_vid_t n_records,
+                          nts_vid_t feature_size, nts_vid_t partition_start,
+                          nts_vid_t partition_end, void *stream);
+
+/* ---- dense-row exchange helpers of the B200 engine (replace the record format on NVLink) -------------- */
+/* dst[k,:] = src[rows[k],:]   (sender-side compaction of mirror rows / pull from a peer's mapped buffer) */
+int nts_gather_rows(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows,
+                    nts_vid_t feature_size, void *stream);
+/* dst[rows[k],:] += src[k,:]  (receiver-side add of partial gradients; rows must be unique) */
+int nts_scatter_add_rows(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows,
+                         nts_vid_t feature_size, void *stream);
+
+/* ---- peer memory (CUDA IPC) for the NVLink exchange ------------------------------------------------------ */
+#define NTS_IPC_HANDLE_BYTES 64
+int nts_ipc_get_handle(void *device_ptr, unsigned char handle[NTS_IPC_HANDLE_BYTES]);
+void *nts_ipc_open_handle(const unsigned char handle[NTS_IPC_HANDLE_BYTES]);
+int nts_ipc_close_handle(void *peer_ptr);
+/* cross-GPU flag signalling on IPC-mapped uint32 flags (release/acquire at system scope) */
+int nts_signal_set(uint32_t *flag, uint32_t value, void *stream);
+int nts_signal_wait_geq(const uint32_t *flag, uint32_t value, void *stream);
+
+/* ---- host-side graph preparation (C++ with OpenMP; no device involved) -----------------------------------
+ * Restates the layout contract of core/graph.hpp:1185-1211 (partitioner), :4396-4401 (degree clamp),
+ * core/ntsBaseOp.hpp:194-197 (edge weight) and core/PartitionedGraph.hpp:324-420 (per-source-partition chunks). */
+/* degrees with multiplicity over packed {u32 src,u32 dst} edges, clamped to >= 1 */
+int nts_host_degrees(const nts_vid_t *edges_src_dst, uint64_t n_edges, nts_vid_t n_vertices,
+                     nts_vid_t *out_degree, nts_vid_t *in_degree);
+/* partition_offset[P+1] */
+int nts_host_partition_offsets(const nts_vid_t *edges_src_dst, uint64_t n_edges, nts_vid_t n_vertices,
+                               int partitions, nts_vid_t *partition_offset);
+/* number of edges of chunk (src partition i -> dst partition p) for every i: counts[P] */
+int nts_host_chunk_edge_counts(const nts_vid_t *edges_src_dst, uint64_t n_edges,
+                               const nts_vid_t *partition_offset, int partitions, int rank,
+                               uint64_t *counts);
+/* build chunk i of rank p into caller-allocated arrays:
+ * column_offset[Vp+1], row_indices[Ei], edge_weight_forward[Ei], row_offset[Vi+1], column_indices[Ei],
+ * edge_weight_backward[Ei], source_active[Vi] (bytes) */
+int nts_host_build_chunk(const nts_vid_t *edges_src_dst, uint64_t n_edges, nts_vid_t n_vertices,
+                         const nts_vid_t *partition_offset, int partitions, int rank, int src_partition,
+                         const nts_vid_t *out_degree, const nts_vid_t *in_degree,
+                         nts_vid_t *column_offset, nts_vid_t *row_indices, float *edge_weight_forward,
+                         nts_vid_t *row_offset, nts_vid_t *column_indices, float *edge_weight_backward,
+                         unsigned char *source_active);
+/* MirrorIndex[V+1] of rank p (core/PartitionedGraph.hpp:295-305); returns owned_mirrors through *owned */
+int nts_host_mirror_index(const nts_vid_t *edges_src_dst, uint64_t n_edges, nts_vid_t n_vertices,
+                          const nts_vid_t *partition_offset, int rank, nts_vid_t *mirror_index,
+                          nts_vid_t *owned);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTS_B200_H */

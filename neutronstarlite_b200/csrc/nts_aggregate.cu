@@ -1,0 +1,477 @@
+// Segmented weighted gather-sum (the SpMM-like neighbour aggregation) for sm_100a.
+//
+//   out[r,:] += sum_{e in [off[r], off[r+1])} in[src(e),:] * w[e]
+//
+// replaces the eight `aggregate_kernel_from_{src,dst}_*` kernels of the reference
+// (cuda/ntsCUDAFuseKernel.cuh:147-487) and their launchers (cuda/ntsCUDAGraphOP.cu:157-281).
+//
+// Design (see DESIGN.md "K1"): HBM/L2-bound gather.  Work is split by EDGES, not rows: warp g owns
+// the edge quantum [q*Q, (q+1)*Q) of column tile t (g = q*tiles + t), finds its first row with a
+// binary search over the offsets, and walks the edges keeping a register accumulator of K vector
+// chunks per lane.  Feature rows are read with 4/8/16-byte vector loads (width picked from F and the
+// pointer alignment: F=602 rows are only 8-byte aligned), U edges are loaded before any FMA so
+// every lane keeps U*K independent loads in flight.  A row that lies entirely inside the quantum is
+// written with one non-atomic read-modify-write; a row cut by a quantum boundary (hubs) is finished
+// with vector `red.global.add` atomics.  No row-degree assumptions, no per-edge atomics, 64-bit
+// address arithmetic throughout.
+//
+// Two index/weight staging variants:
+//   variant 1 (shuffle): each lane loads one edge's (index, weight) coalesced, broadcast by __shfl.
+//   variant 2 (bulk):    one thread per CTA issues `cp.async.bulk` (TMA, SASS UBLKCP) copies of the
+//                        CTA's index and weight tiles into shared memory, completion on an mbarrier;
+//                        warps then read (index, weight) with broadcast LDS.
+#include "nts_common.cuh"
+
+namespace nts {
+
+static int g_variant = 0;          // 0 = auto
+static int g_edges_per_warp = 0;   // 0 = auto
+static int g_last_grid = 0, g_last_block = 0, g_last_smem = 0, g_last_variant = 0;
+
+// ---- small device helpers --------------------------------------------------------------------------------
+template <int VEC> __device__ __forceinline__ typename Vec<VEC>::type ldg_vec(const typename Vec<VEC>::type *p) {
+  return __ldg(p);
+}
+
+__device__ __forceinline__ void fma_vec(float &a, float w, float x) { a = fmaf(w, x, a); }
+__device__ __forceinline__ void fma_vec(float2 &a, float w, float2 x) {
+  a.x = fmaf(w, x.x, a.x);
+  a.y = fmaf(w, x.y, a.y);
+}
+__device__ __forceinline__ void fma_vec(float4 &a, float w, float4 x) {
+  a.x = fmaf(w, x.x, a.x);
+  a.y = fmaf(w, x.y, a.y);
+  a.z = fmaf(w, x.z, a.z);
+  a.w = fmaf(w, x.w, a.w);
+}
+__device__ __forceinline__ void zero_vec(float &a) { a = 0.f; }
+__device__ __forceinline__ void zero_vec(float2 &a) { a = make_float2(0.f, 0.f); }
+__device__ __forceinline__ void zero_vec(float4 &a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ void rmw_add(float *p, float a) { *p = *p + a; }
+__device__ __forceinline__ void rmw_add(float2 *p, float2 a) {
+  float2 o = *p;
+  o.x += a.x;
+  o.y += a.y;
+  *p = o;
+}
+__device__ __forceinline__ void rmw_add(float4 *p, float4 a) {
+  float4 o = *p;
+  o.x += a.x;
+  o.y += a.y;
+  o.z += a.z;
+  o.w += a.w;
+  *p = o;
+}
+// no-return vector reductions (sm_90+): one L2 atomic transaction per 8/16 bytes
+__device__ __forceinline__ void red_add(float *p, float a) { atomicAdd(p, a); }
+__device__ __forceinline__ void red_add(float2 *p, float2 a) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a.x), "f"(a.y) : "memory");
+}
+__device__ __forceinline__ void red_add(float4 *p, float4 a) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+               : "memory");
+}
+
+// largest r in [0, n_rows) with off[r] <= e  (requires off[0] <= e < off[n_rows])
+__device__ __forceinline__ uint32_t find_row(const uint32_t *__restrict__ off, uint32_t n_rows, uint32_t e) {
+  uint32_t lo = 0, hi = n_rows; // invariant: off[lo] <= e < off[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(off + mid) <= e)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// mbarrier / bulk-copy PTX (variant 2)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile("{\n\t"
+               ".reg .pred p;\n\t"
+               "WAIT_%=:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@p bra DONE_%=;\n\t"
+               "bra WAIT_%=;\n\t"
+               "DONE_%=:\n\t"
+               "}" ::"r"(smem_u32(bar)),
+               "r"(parity)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kWarpsPerBlock = 8;
+
+// ---- the kernel --------------------------------------------------------------------------------------------
+// VEC  : floats per vector load (1, 2, 4); feature_size % VEC == 0 and rows VEC*4-byte aligned
+// K    : vector chunks per lane per column tile (a tile covers K*32*VEC floats)
+// U    : edges loaded before the FMAs start (memory-level parallelism = U*K loads per lane)
+// BULK : stage index/weight tiles with cp.async.bulk + mbarrier (variant 2)
+template <int VEC, int K, int U, bool BULK>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    segment_gather_sum_kernel(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ w,
+                              const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
+                              const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
+                              uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t n_edges = (uint32_t)n_edges64;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp_in_block = threadIdx.x >> 5;
+  const uint32_t nvec = F / VEC;
+
+  // quantum / tile owned by this warp.  In BULK mode all warps of a CTA share one column tile range
+  // layout: consecutive warps = consecutive tiles of the same quantum, so one CTA covers
+  // kWarpsPerBlock/tiles... (kept simple: CTA covers quanta [cta_q0, cta_q0 + quanta_per_cta)).
+  const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp_in_block;
+  const uint32_t tile = (uint32_t)(gwarp % tiles);
+  const uint64_t q = gwarp / tiles;
+  const uint64_t e0_64 = q * (uint64_t)Q;
+
+  // BULK staging buffers: indices+weights of every edge this CTA touches
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *s_idx = nullptr;
+  float *s_w = nullptr;
+  uint32_t cta_e_base = 0; // first staged edge (16-byte aligned element index)
+  uint32_t bulk_bytes = 0;
+  if constexpr (BULK) {
+    // CTA edge span: quanta of warps 0..kWarpsPerBlock-1
+    const uint64_t first_q = ((uint64_t)blockIdx.x * kWarpsPerBlock) / tiles;
+    const uint64_t last_q = ((uint64_t)blockIdx.x * kWarpsPerBlock + kWarpsPerBlock - 1) / tiles;
+    uint64_t ce0 = first_q * (uint64_t)Q;
+    uint64_t ce1 = (last_q + 1) * (uint64_t)Q;
+    if (ce1 > n_edges)
+      ce1 = n_edges;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    const uint32_t span_cap = (kWarpsPerBlock / 1) * Q + 8; // elements reserved per array (host sizes smem to this)
+    s_idx = reinterpret_cast<uint32_t *>(smem_raw + 16);
+    s_w = reinterpret_cast<float *>(smem_raw + 16 + (size_t)span_cap * 4);
+    if (ce0 < ce1) {
+      cta_e_base = (uint32_t)(ce0 & ~3ull); // 16-byte aligned start (arrays are 16-byte aligned)
+      const uint32_t n_el = (uint32_t)(ce1 - cta_e_base);
+      bulk_bytes = (n_el * 4u) & ~15u;      // whole 16-byte units go through the bulk engine ...
+      const uint32_t bulk_el = bulk_bytes / 4u;
+      if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      if (threadIdx.x < n_el - bulk_el) {   // ... the last < 4 elements by plain loads (never read past the array)
+        s_idx[bulk_el + threadIdx.x] = __ldg(idx + cta_e_base + bulk_el + threadIdx.x);
+        if (w)
+          s_w[bulk_el + threadIdx.x] = __ldg(w + cta_e_base + bulk_el + threadIdx.x);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0 && bulk_bytes) {
+        mbar_expect_tx(bar, w ? 2 * bulk_bytes : bulk_bytes);
+        bulk_g2s(s_idx, idx + cta_e_base, bulk_bytes, bar);
+        if (w)
+          bulk_g2s(s_w, w + cta_e_base, bulk_bytes, bar);
+      }
+    }
+  }
+
+  if (e0_64 >= n_edges64) {
+    return; // (BULK: a CTA whose later warps have no work still issued/awaited nothing they need)
+  }
+  const uint32_t e0 = (uint32_t)e0_64;
+  const uint32_t e1 = (e0_64 + Q < n_edges64) ? e0 + Q : n_edges;
+
+  // column tile handled by this warp
+  const uint32_t c0 = tile * (K * 32) + lane; // first vector column of this lane
+  bool act[K];
+#pragma unroll
+  for (int k = 0; k < K; k++)
+    act[k] = (c0 + k * 32) < nvec;
+
+  // first row of the quantum (overlaps with the bulk copy in flight)
+  uint32_t row = find_row(off, n_rows, e0);
+  uint32_t row_end = __ldg(off + row + 1);
+  bool row_started_inside = __ldg(off + row) >= e0;
+
+  V acc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++)
+    zero_vec(acc[k]);
+
+  auto flush = [&](bool whole) {
+    V *o = reinterpret_cast<V *>(out + (size_t)row * F) + c0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (act[k]) {
+        if (whole)
+          rmw_add(o + k * 32, acc[k]);
+        else
+          red_add(o + k * 32, acc[k]);
+      }
+      zero_vec(acc[k]);
+    }
+  };
+  // move to the row containing edge ee (ee >= row_end on entry)
+  auto advance = [&](uint32_t ee) {
+    flush(row_started_inside); // row_end <= ee < e1: the row ends inside the quantum
+    do {
+      row++;
+      row_end = __ldg(off + row + 1);
+    } while (ee >= row_end);
+    row_started_inside = true;
+  };
+
+  if constexpr (BULK) {
+    if (bulk_bytes)
+      mbar_wait(reinterpret_cast<uint64_t *>(smem_raw), 0);
+  }
+
+  for (uint32_t e = e0; e < e1; e += 32) {
+    const uint32_t cnt = min(32u, e1 - e);
+    uint32_t my_src = 0;
+    float my_w = 1.f;
+    if constexpr (!BULK) {
+      if (lane < cnt) {
+        uint32_t id = __ldg(idx + e + lane);
+        my_src = slot_of ? __ldg(slot_of + id) : id - base;
+        if (w)
+          my_w = __ldg(w + e + lane);
+      }
+    }
+    uint32_t j = 0;
+    // full groups of U edges: U*K independent vector loads per lane, then the FMAs
+    for (; j + U <= cnt; j += U) {
+      V v[U][K];
+      float wu[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        uint32_t s;
+        if constexpr (BULK) {
+          uint32_t id = s_idx[e + j + u - cta_e_base];
+          s = slot_of ? __ldg(slot_of + id) : id - base;
+          wu[u] = w ? s_w[e + j + u - cta_e_base] : 1.f;
+        } else {
+          s = __shfl_sync(0xffffffffu, my_src, j + u);
+          wu[u] = __shfl_sync(0xffffffffu, my_w, j + u);
+        }
+        const V *p = reinterpret_cast<const V *>(in + (size_t)s * F) + c0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if (act[k])
+            v[u][k] = ldg_vec<VEC>(p + k * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t ee = e + j + u;
+        if (ee >= row_end)
+          advance(ee);
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if (act[k])
+            fma_vec(acc[k], wu[u], v[u][k]);
+      }
+    }
+    // remainder (< U edges)
+    for (; j < cnt; j++) {
+      uint32_t s;
+      float wj;
+      if constexpr (BULK) {
+        uint32_t id = s_idx[e + j - cta_e_base];
+        s = slot_of ? __ldg(slot_of + id) : id - base;
+        wj = w ? s_w[e + j - cta_e_base] : 1.f;
+      } else {
+        s = __shfl_sync(0xffffffffu, my_src, j);
+        wj = __shfl_sync(0xffffffffu, my_w, j);
+      }
+      const V *p = reinterpret_cast<const V *>(in + (size_t)s * F) + c0;
+      V v1[K];
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        if (act[k])
+          v1[k] = ldg_vec<VEC>(p + k * 32);
+      const uint32_t ee = e + j;
+      if (ee >= row_end)
+        advance(ee);
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        if (act[k])
+          fma_vec(acc[k], wj, v1[k]);
+    }
+  }
+  // last row of the quantum: whole only if it started inside and also ends at/before e1
+  flush(row_started_inside && row_end <= e1);
+}
+
+// ---- host-side dispatch ---------------------------------------------------------------------------------
+struct LaunchShape {
+  int vec, k, u;
+  uint32_t tiles;
+};
+
+static LaunchShape pick_shape(const float *in, const float *out, uint32_t F) {
+  LaunchShape s;
+  bool a16 = aligned_to(in, 16) && aligned_to(out, 16);
+  bool a8 = aligned_to(in, 8) && aligned_to(out, 8);
+  if (F % 4 == 0 && a16)
+    s.vec = 4;
+  else if (F % 2 == 0 && a8)
+    s.vec = 2;
+  else
+    s.vec = 1;
+  uint32_t nvec = F / s.vec;
+  uint32_t chunks = (nvec + 31) / 32;
+  // chunks per lane per tile: balance tiles so the last one is not nearly empty
+  const uint32_t kmax = (s.vec == 4) ? 4 : 5;
+  s.tiles = (chunks + kmax - 1) / kmax;
+  s.k = (int)((chunks + s.tiles - 1) / s.tiles);
+  s.tiles = (chunks + s.k - 1) / s.k;
+  // loads in flight per lane ~ 32-40 floats
+  int budget = 40 / (s.k * s.vec);
+  s.u = budget >= 8 ? 8 : (budget >= 4 ? 4 : 2);
+  return s;
+}
+
+template <int VEC, int K, int U>
+static int launch_shape(bool bulk, const float *in, float *out, const float *w, const uint32_t *idx,
+                        const uint32_t *off, const uint32_t *slot_of, uint32_t base, uint32_t n_rows,
+                        uint64_t n_edges, uint32_t F, uint32_t Q, uint32_t tiles, cudaStream_t st) {
+  uint64_t quanta = (n_edges + Q - 1) / Q;
+  uint64_t warps = quanta * tiles;
+  uint64_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  NTS_ARG_CHECK(blocks <= 0x7fffffffull, "aggregation grid too large");
+  g_last_grid = (int)blocks;
+  g_last_block = kWarpsPerBlock * 32;
+  if (bulk) {
+    size_t span_cap = (size_t)kWarpsPerBlock * Q + 8;
+    size_t smem = 16 + 2 * span_cap * 4;
+    auto kern = segment_gather_sum_kernel<VEC, K, U, true>;
+    NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    g_last_smem = (int)smem;
+    kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F,
+                                                              Q, tiles);
+  } else {
+    g_last_smem = 0;
+    segment_gather_sum_kernel<VEC, K, U, false>
+        <<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q,
+                                                           tiles);
+  }
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+#define NTS_SHAPE_CASE(V_, K_, U_)                                                                            \
+  if (s.vec == V_ && s.k == K_ && s.u == U_)                                                                   \
+    return launch_shape<V_, K_, U_>(bulk, in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, s.tiles, st);
+
+static int segment_gather_sum(const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *off,
+                              const uint32_t *slot_of, uint32_t base, uint32_t n_rows, uint64_t n_edges, uint32_t F,
+                              cudaStream_t st) {
+  if (n_rows == 0 || n_edges == 0 || F == 0)
+    return 0;
+  NTS_ARG_CHECK(in && out && idx && off, "null pointer passed to segment_gather_sum");
+  NTS_ARG_CHECK(n_edges < 0xffffffffull, "chunk edge count must fit uint32 offsets");
+  LaunchShape s = pick_shape(in, out, F);
+  // edges per warp: multiple of 32; shrink for small inputs so the grid still fills 148 SMs
+  uint32_t Q = g_edges_per_warp > 0 ? (uint32_t)g_edges_per_warp : 256u;
+  if (g_edges_per_warp <= 0) {
+    const uint64_t want_warps = (uint64_t)sm_count() * 64;
+    while (Q > 32 && ((n_edges + Q - 1) / Q) * s.tiles < want_warps)
+      Q >>= 1;
+  }
+  Q = (Q + 31u) & ~31u;
+  int variant = g_variant == 0 ? 1 : g_variant;
+  bool bulk = variant == 2;
+  // the bulk copies need 16-byte aligned index/weight arrays (cudaMalloc gives 256)
+  if (bulk && !(aligned_to(idx, 16) && (!w || aligned_to(w, 16)))) {
+    bulk = false;
+    variant = 1;
+  }
+  g_last_variant = variant;
+  NTS_SHAPE_CASE(4, 1, 8)
+  NTS_SHAPE_CASE(4, 2, 4)
+  NTS_SHAPE_CASE(4, 3, 2)
+  NTS_SHAPE_CASE(4, 4, 2)
+  NTS_SHAPE_CASE(2, 1, 8)
+  NTS_SHAPE_CASE(2, 2, 8)
+  NTS_SHAPE_CASE(2, 3, 4)
+  NTS_SHAPE_CASE(2, 4, 4)
+  NTS_SHAPE_CASE(2, 5, 4)
+  NTS_SHAPE_CASE(1, 1, 8)
+  NTS_SHAPE_CASE(1, 2, 8)
+  NTS_SHAPE_CASE(1, 3, 8)
+  NTS_SHAPE_CASE(1, 4, 8)
+  NTS_SHAPE_CASE(1, 5, 8)
+  return fail(-1, "no kernel instantiation for this feature width", __FILE__, __LINE__);
+}
+
+} // namespace nts
+
+extern "C" {
+
+int nts_segment_gather_sum(const float *input, float *output, const float *weight, const nts_vid_t *indices,
+                           const nts_vid_t *offsets, nts_vid_t index_base, nts_vid_t n_rows, uint64_t n_edges,
+                           nts_vid_t feature_size, void *stream) {
+  return nts::segment_gather_sum(input, output, weight, indices, offsets, nullptr, index_base, n_rows, n_edges,
+                                 feature_size, nts::as_stream(stream));
+}
+
+int nts_segment_gather_sum_slots(const float *input, float *output, const float *weight, const nts_vid_t *indices,
+                                 const nts_vid_t *offsets, const nts_vid_t *slot_of, nts_vid_t n_rows,
+                                 uint64_t n_edges, nts_vid_t feature_size, void *stream) {
+  NTS_ARG_CHECK(slot_of != nullptr, "slot table is null");
+  return nts::segment_gather_sum(input, output, weight, indices, offsets, slot_of, 0, n_rows, n_edges, feature_size,
+                                 nts::as_stream(stream));
+}
+
+int nts_gather_by_dst_from_src(const float *input, float *output, const float *weight_forward,
+                               const nts_vid_t *row_indices, const nts_vid_t *column_offset, nts_vid_t src_start,
+                               nts_vid_t src_end, nts_vid_t dst_start, nts_vid_t dst_end, nts_vid_t edges,
+                               nts_vid_t batch_size, nts_vid_t feature_size, int with_weight, void *stream) {
+  (void)src_end;
+  (void)dst_start;
+  (void)dst_end;
+  NTS_ARG_CHECK(!with_weight || weight_forward, "with_weight set but weight pointer is null");
+  return nts::segment_gather_sum(input, output, with_weight ? weight_forward : nullptr, row_indices, column_offset,
+                                 nullptr, src_start, batch_size, edges, feature_size, nts::as_stream(stream));
+}
+
+int nts_gather_by_src_from_dst(const float *input, float *output, const float *weight_backward,
+                               const nts_vid_t *row_offset, const nts_vid_t *column_indices, nts_vid_t src_start,
+                               nts_vid_t src_end, nts_vid_t dst_start, nts_vid_t dst_end, nts_vid_t edges,
+                               nts_vid_t batch_size, nts_vid_t feature_size, int with_weight, void *stream) {
+  (void)src_start;
+  (void)src_end;
+  (void)dst_end;
+  NTS_ARG_CHECK(!with_weight || weight_backward, "with_weight set but weight pointer is null");
+  return nts::segment_gather_sum(input, output, with_weight ? weight_backward : nullptr, column_indices, row_offset,
+                                 nullptr, dst_start, batch_size, edges, feature_size, nts::as_stream(stream));
+}
+
+int nts_aggregate_set_variant(int variant, int edges_per_warp) {
+  NTS_ARG_CHECK(variant >= 0 && variant <= 2, "variant must be 0 (auto), 1 (shuffle) or 2 (bulk)");
+  NTS_ARG_CHECK(edges_per_warp >= 0 && edges_per_warp <= 4096, "edges_per_warp out of range");
+  nts::g_variant = variant;
+  nts::g_edges_per_warp = edges_per_warp;
+  return 0;
+}
+
+int nts_aggregate_last_launch(int *grid, int *block, int *smem_bytes, int *variant) {
+  if (grid)
+    *grid = nts::g_last_grid;
+  if (block)
+    *block = nts::g_last_block;
+  if (smem_bytes)
+    *smem_bytes = nts::g_last_smem;
+  if (variant)
+    *variant = nts::g_last_variant;
+  return 0;
+}
+
+} // extern "C"

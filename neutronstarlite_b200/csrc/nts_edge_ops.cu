@@ -1,0 +1,549 @@
+// Edge-granular operators of the GAT path for sm_100a: mirror/destination <-> edge-message copies,
+// per-destination edge softmax (multi-column, max-subtracted) and the fused-aggregation backward.
+//
+// Replaces cuda/ntsCUDADistKernel.cuh:23-95,166-260 and the `scatter_grad_back_to_messaage` kernel
+// (cuda/ntsCUDAFuseKernel.cuh:492-506) of the reference.  These kernels are HBM-bound streams over
+// [E, F] messages: every one moves whole rows with the widest vector the row alignment allows, is
+// split by EDGES (a warp owns a quantum of consecutive edges and finds its destination rows by
+// binary search over column_offset), and uses atomics only where two edges of different
+// destinations meet in one mirror row.
+#include "nts_common.cuh"
+
+namespace nts {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kEdgeQuantum = 64; // consecutive edges per warp
+
+__device__ __forceinline__ uint32_t eo_find_row(const uint32_t *__restrict__ off, uint32_t n_rows, uint32_t e) {
+  uint32_t lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (__ldg(off + mid) <= e)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+template <int VEC> __device__ __forceinline__ void vec_red_add(typename Vec<VEC>::type *p, typename Vec<VEC>::type a);
+template <> __device__ __forceinline__ void vec_red_add<1>(float *p, float a) { atomicAdd(p, a); }
+template <> __device__ __forceinline__ void vec_red_add<2>(float2 *p, float2 a) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a.x), "f"(a.y) : "memory");
+}
+template <> __device__ __forceinline__ void vec_red_add<4>(float4 *p, float4 a) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+               : "memory");
+}
+__device__ __forceinline__ float vec_dot(float a, float b) { return a * b; }
+__device__ __forceinline__ float vec_dot(float2 a, float2 b) { return fmaf(a.x, b.x, a.y * b.y); }
+__device__ __forceinline__ float vec_dot(float4 a, float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float vec_scale(float a, float s) { return a * s; }
+__device__ __forceinline__ float2 vec_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float4 vec_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float vec_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 vec_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float4 vec_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// ---- row movers ------------------------------------------------------------------------------------------
+// mode 0: dst[r,:]        = src[map(r),:]
+// mode 1: dst[map(r),:]  += src[r,:]   (map unique -> plain read-modify-write)
+// mode 2: dst[map(r),:]  += src[r,:]   (atomic)
+// map(r) = map2 ? map2[map1[r]] : map1[r]
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(kThreads)
+    move_rows_kernel(float *__restrict__ dst, const float *__restrict__ src, const uint32_t *__restrict__ map1,
+                     const uint32_t *__restrict__ map2, uint64_t n_rows, const uint32_t *__restrict__ n_rows_dev,
+                     uint32_t F) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nvec = F / VEC;
+  if (n_rows_dev)
+    n_rows = __ldg(n_rows_dev); // e.g. E_p = column_offset[Vp], kept on the device
+  const uint64_t warp0 = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t r = warp0; r < n_rows; r += nwarps) {
+    uint32_t m = __ldg(map1 + r);
+    if (map2)
+      m = __ldg(map2 + m);
+    if (MODE == 0) {
+      const V *s = reinterpret_cast<const V *>(src + (size_t)m * F);
+      V *d = reinterpret_cast<V *>(dst + (size_t)r * F);
+      for (uint32_t c = lane; c < nvec; c += 32)
+        d[c] = __ldg(s + c);
+    } else {
+      const V *s = reinterpret_cast<const V *>(src + (size_t)r * F);
+      V *d = reinterpret_cast<V *>(dst + (size_t)m * F);
+      for (uint32_t c = lane; c < nvec; c += 32) {
+        V v = __ldg(s + c);
+        if (MODE == 1)
+          d[c] = vec_add(d[c], v);
+        else
+          vec_red_add<VEC>(d + c, v);
+      }
+    }
+  }
+}
+
+// msg[e,:] (=|+=) x[dst(e),:] : destination row broadcast over its CSC segment
+template <int VEC, bool ACCUM>
+__global__ void __launch_bounds__(kThreads)
+    segment_broadcast_kernel(float *__restrict__ msg, const float *__restrict__ x, const uint32_t *__restrict__ off,
+                             uint32_t n_rows, uint32_t F) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nvec = F / VEC;
+  const uint32_t n_edges = __ldg(off + n_rows); // E_p stays on the device: no host read-back
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kEdgeQuantum < n_edges; qw += nwarps) {
+  const uint32_t e0 = (uint32_t)(qw * kEdgeQuantum);
+  const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kEdgeQuantum);
+  uint32_t row = eo_find_row(off, n_rows, e0);
+  uint32_t row_end = __ldg(off + row + 1);
+  for (uint32_t e = e0; e < e1; e++) {
+    while (e >= row_end) {
+      row++;
+      row_end = __ldg(off + row + 1);
+    }
+    const V *s = reinterpret_cast<const V *>(x + (size_t)row * F);
+    V *d = reinterpret_cast<V *>(msg + (size_t)e * F);
+    for (uint32_t c = lane; c < nvec; c += 32) {
+      V v = __ldg(s + c);
+      d[c] = ACCUM ? vec_add(d[c], v) : v;
+    }
+  }
+  } // quantum loop
+}
+
+// y[d,:] += sum_{e->d} msg[e,:]: edge-quantum segmented sum of a contiguous stream; boundary rows use atomics
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    segment_sum_kernel(float *__restrict__ y, const float *__restrict__ msg, const uint32_t *__restrict__ off,
+                       uint32_t n_rows, uint32_t F) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nvec = F / VEC;
+  const uint32_t n_edges = __ldg(off + n_rows); // E_p stays on the device: no host read-back
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kEdgeQuantum < n_edges; qw += nwarps) {
+  const uint32_t e0 = (uint32_t)(qw * kEdgeQuantum);
+  const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kEdgeQuantum);
+  // columns are processed in passes of 32 vectors so that the accumulator stays in one register set
+  for (uint32_t cbase = 0; cbase < nvec; cbase += 32) {
+    const uint32_t c = cbase + lane;
+    const bool act = c < nvec;
+    uint32_t row = eo_find_row(off, n_rows, e0);
+    uint32_t row_end = __ldg(off + row + 1);
+    bool inside = __ldg(off + row) >= e0;
+    V acc;
+    memset(&acc, 0, sizeof(V));
+    for (uint32_t e = e0; e < e1; e++) {
+      if (e >= row_end) {
+        if (act) {
+          V *o = reinterpret_cast<V *>(y + (size_t)row * F) + c;
+          if (inside)
+            *o = vec_add(*o, acc);
+          else
+            vec_red_add<VEC>(o, acc);
+        }
+        memset(&acc, 0, sizeof(V));
+        do {
+          row++;
+          row_end = __ldg(off + row + 1);
+        } while (e >= row_end);
+        inside = true;
+      }
+      if (act)
+        acc = vec_add(acc, __ldg(reinterpret_cast<const V *>(msg + (size_t)e * F) + c));
+    }
+    if (act) {
+      V *o = reinterpret_cast<V *>(y + (size_t)row * F) + c;
+      if (inside && row_end <= e1)
+        *o = vec_add(*o, acc);
+      else
+        vec_red_add<VEC>(o, acc);
+    }
+  }
+  } // quantum loop
+}
+
+// ---- edge softmax ------------------------------------------------------------------------------------------
+// One CTA walks a block of destination rows.  Small segments are handled one per warp, segments with
+// more than kHubDegree edges by the whole CTA.  H = number of columns (heads); element (e,h) at m[e*H+h].
+constexpr uint32_t kRowsPerCta = 64;
+constexpr uint32_t kHubDegree = 4096;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool IS_MAX> __device__ __forceinline__ float block_reduce(float v, float *scratch) {
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads(); // scratch reuse
+  if (lane == 0)
+    scratch[wid] = v;
+  __syncthreads();
+  float r = scratch[0];
+#pragma unroll
+  for (int i = 1; i < kWarps; i++)
+    r = IS_MAX ? fmaxf(r, scratch[i]) : r + scratch[i];
+  return r;
+}
+
+// forward: a = exp(m - max) / sum exp(m - max) per (segment, column); cache gets a copy of a
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kThreads)
+    edge_softmax_kernel(float *__restrict__ out, const float *__restrict__ in0, const float *__restrict__ in1,
+                        float *__restrict__ cache, const uint32_t *__restrict__ off, uint32_t n_rows, uint32_t H) {
+  // forward : in0 = m,      in1 unused, out = a, cache = a
+  // backward: in0 = g_out,  in1 = a (cached), out = g_in = a*g - a*sum(a*g)
+  __shared__ float scratch[kWarps];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t r0 = blockIdx.x * kRowsPerCta;
+  const uint32_t r1 = min(n_rows, r0 + kRowsPerCta);
+  for (uint32_t r = r0; r < r1; r++) {
+    const uint32_t b = __ldg(off + r), e = __ldg(off + r + 1);
+    const uint32_t deg = e - b;
+    if (deg == 0)
+      continue;
+    const bool hub = deg > kHubDegree; // block-uniform
+    if (!hub && ((r - r0) % kWarps) != wid)
+      continue;
+    const uint32_t tid = hub ? threadIdx.x : lane;
+    const uint32_t nthr = hub ? kThreads : 32;
+    for (uint32_t h = 0; h < H; h++) {
+      const float *x0 = in0 + (size_t)b * H + h;
+      if (!BACKWARD) {
+        float mx = -INFINITY;
+        for (uint32_t i = tid; i < deg; i += nthr)
+          mx = fmaxf(mx, __ldg(x0 + (size_t)i * H));
+        mx = hub ? block_reduce<true>(mx, scratch) : warp_max(mx);
+        float s = 0.f;
+        for (uint32_t i = tid; i < deg; i += nthr)
+          s += expf(__ldg(x0 + (size_t)i * H) - mx);
+        s = hub ? block_reduce<false>(s, scratch) : warp_sum(s);
+        const float inv = 1.f / s;
+        for (uint32_t i = tid; i < deg; i += nthr) {
+          float a = expf(__ldg(x0 + (size_t)i * H) - mx) * inv;
+          out[((size_t)b + i) * H + h] = a;
+          if (cache)
+            cache[((size_t)b + i) * H + h] = a;
+        }
+      } else {
+        const float *a0 = in1 + (size_t)b * H + h;
+        float dot = 0.f;
+        for (uint32_t i = tid; i < deg; i += nthr)
+          dot = fmaf(__ldg(x0 + (size_t)i * H), __ldg(a0 + (size_t)i * H), dot);
+        dot = hub ? block_reduce<false>(dot, scratch) : warp_sum(dot);
+        for (uint32_t i = tid; i < deg; i += nthr) {
+          float a = __ldg(a0 + (size_t)i * H);
+          float g = __ldg(x0 + (size_t)i * H);
+          out[((size_t)b + i) * H + h] = a * g - a * dot;
+        }
+      }
+    }
+  }
+}
+
+// ---- fused GAT aggregation backward ----------------------------------------------------------------------
+//   a_grad[e]               = < mirror[slot(e),:], g[dst(e),:] >      (warp-shuffle reduction)
+//   mirror_grad[slot(e),:] += a[e] * g[dst(e),:]                      (vector red.global.add)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    fuse_weight_backward_kernel(float *__restrict__ mirror_grad, float *__restrict__ a_grad,
+                                const float *__restrict__ mirror, const float *__restrict__ a,
+                                const float *__restrict__ g, const uint32_t *__restrict__ row_idx,
+                                const uint32_t *__restrict__ off, const uint32_t *__restrict__ mirror_index,
+                                uint32_t n_rows, uint32_t F) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nvec = F / VEC;
+  const uint32_t n_edges = __ldg(off + n_rows); // E_p stays on the device: no host read-back
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kEdgeQuantum < n_edges; qw += nwarps) {
+  const uint32_t e0 = (uint32_t)(qw * kEdgeQuantum);
+  const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kEdgeQuantum);
+  uint32_t row = eo_find_row(off, n_rows, e0);
+  uint32_t row_end = __ldg(off + row + 1);
+  for (uint32_t e = e0; e < e1; e++) {
+    while (e >= row_end) {
+      row++;
+      row_end = __ldg(off + row + 1);
+    }
+    const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
+    const float ae = __ldg(a + e);
+    const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F);
+    const V *mm = reinterpret_cast<const V *>(mirror + (size_t)slot * F);
+    V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F);
+    float dot = 0.f;
+    for (uint32_t c = lane; c < nvec; c += 32) {
+      V gv = __ldg(gm + c);
+      dot += vec_dot(__ldg(mm + c), gv);
+      vec_red_add<VEC>(dm + c, vec_scale(gv, ae));
+    }
+    dot = warp_sum(dot);
+    if (lane == 0)
+      a_grad[e] = dot;
+  }
+  } // quantum loop
+}
+
+// ---- (vid,row) records read from mapped pinned host memory ---------------------------------------------------
+template <bool ACCUM>
+__global__ void __launch_bounds__(kThreads)
+    records_kernel(float *__restrict__ dst, const float *__restrict__ records, uint32_t n_records, uint32_t F,
+                   uint32_t start, uint32_t end) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp0 = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  const size_t stride = (size_t)F + 1;
+  for (uint64_t k = warp0; k < n_records; k += nwarps) {
+    const float *rec = records + k * stride;
+    const uint32_t vid = reinterpret_cast<const uint32_t *>(rec)[0];
+    if (vid < start || vid >= end)
+      continue;
+    float *d = dst + (size_t)(vid - start) * F;
+    for (uint32_t c = lane; c < F; c += 32) {
+      float v = rec[1 + c];
+      if (ACCUM)
+        atomicAdd(d + c, v);
+      else
+        d[c] = v;
+    }
+  }
+}
+
+// ---- launch helpers ----------------------------------------------------------------------------------------
+static int pick_vec(uint32_t F, const void *a, const void *b, const void *c = nullptr) {
+  bool a16 = aligned_to(a, 16) && aligned_to(b, 16) && (!c || aligned_to(c, 16));
+  bool a8 = aligned_to(a, 8) && aligned_to(b, 8) && (!c || aligned_to(c, 8));
+  if (F % 4 == 0 && a16)
+    return 4;
+  if (F % 2 == 0 && a8)
+    return 2;
+  return 1;
+}
+
+// persistent-style grid: enough CTAs to fill every SM several times over, work is grid-strided
+static unsigned stream_grid(uint64_t rows) {
+  uint64_t blocks = (rows + kWarps - 1) / kWarps;
+  uint64_t cap = (uint64_t)sm_count() * 16;
+  if (blocks > cap)
+    blocks = cap;
+  if (blocks == 0)
+    blocks = 1;
+  return (unsigned)blocks;
+}
+static unsigned full_grid() { return (unsigned)(sm_count() * 16); }
+
+template <int MODE>
+static int move_rows(float *dst, const float *src, const uint32_t *map1, const uint32_t *map2, uint64_t n_rows,
+                     const uint32_t *n_rows_dev, uint32_t F, cudaStream_t st) {
+  if ((n_rows == 0 && !n_rows_dev) || F == 0)
+    return 0;
+  NTS_ARG_CHECK(dst && src && map1, "null pointer passed to row mover");
+  int vec = pick_vec(F, dst, src);
+  unsigned grid = n_rows_dev ? full_grid() : stream_grid(n_rows);
+  if (vec == 4)
+    move_rows_kernel<4, MODE><<<grid, kThreads, 0, st>>>(dst, src, map1, map2, n_rows, n_rows_dev, F);
+  else if (vec == 2)
+    move_rows_kernel<2, MODE><<<grid, kThreads, 0, st>>>(dst, src, map1, map2, n_rows, n_rows_dev, F);
+  else
+    move_rows_kernel<1, MODE><<<grid, kThreads, 0, st>>>(dst, src, map1, map2, n_rows, n_rows_dev, F);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+} // namespace nts
+
+using namespace nts;
+
+extern "C" {
+
+int nts_gather_rows(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows, nts_vid_t feature_size,
+                    void *stream) {
+  return move_rows<0>(dst, src, rows, nullptr, n_rows, nullptr, feature_size, as_stream(stream));
+}
+
+int nts_scatter_add_rows(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows,
+                         nts_vid_t feature_size, void *stream) {
+  return move_rows<1>(dst, src, rows, nullptr, n_rows, nullptr, feature_size, as_stream(stream));
+}
+
+// The edge count E_p = column_offset[batch_size] is read by the kernels on the device (the reference keeps
+// e_size on the host inside deviceCSC; its Cuda_Stream signatures do not pass it).
+int nts_scatter_src_mirror_to_msg(float *message, const float *src_mirror_feature, const nts_vid_t *row_indices,
+                                  const nts_vid_t *column_offset, const nts_vid_t *mirror_index,
+                                  nts_vid_t batch_size, nts_vid_t feature_size, void *stream) {
+  if (batch_size == 0)
+    return 0;
+  NTS_ARG_CHECK(column_offset && mirror_index, "null graph pointer");
+  return move_rows<0>(message, src_mirror_feature, row_indices, mirror_index, 0, column_offset + batch_size,
+                      feature_size, as_stream(stream));
+}
+
+int nts_gather_msg_to_src_mirror(float *src_mirror_feature, const float *message, const nts_vid_t *row_indices,
+                                 const nts_vid_t *column_offset, const nts_vid_t *mirror_index,
+                                 nts_vid_t batch_size, nts_vid_t feature_size, void *stream) {
+  if (batch_size == 0)
+    return 0;
+  NTS_ARG_CHECK(column_offset && mirror_index, "null graph pointer");
+  return move_rows<2>(src_mirror_feature, message, row_indices, mirror_index, 0, column_offset + batch_size,
+                      feature_size, as_stream(stream));
+}
+
+static int segment_broadcast(float *msg, const float *x, const nts_vid_t *column_offset, nts_vid_t batch_size,
+                             nts_vid_t F, bool accum, cudaStream_t st) {
+  if (batch_size == 0 || F == 0)
+    return 0;
+  NTS_ARG_CHECK(msg && x && column_offset, "null pointer passed to segment broadcast");
+  int vec = pick_vec(F, msg, x);
+  unsigned grid = full_grid();
+#define NTS_BCAST(V_)                                                                                     \
+  if (accum)                                                                                              \
+    segment_broadcast_kernel<V_, true><<<grid, kThreads, 0, st>>>(msg, x, column_offset, batch_size, F);  \
+  else                                                                                                    \
+    segment_broadcast_kernel<V_, false><<<grid, kThreads, 0, st>>>(msg, x, column_offset, batch_size, F);
+  if (vec == 4) {
+    NTS_BCAST(4)
+  } else if (vec == 2) {
+    NTS_BCAST(2)
+  } else {
+    NTS_BCAST(1)
+  }
+#undef NTS_BCAST
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_scatter_dst_to_msg(float *message, const float *dst_feature, const nts_vid_t *row_indices,
+                           const nts_vid_t *column_offset, nts_vid_t batch_size, nts_vid_t feature_size,
+                           void *stream) {
+  (void)row_indices;
+  return segment_broadcast(message, dst_feature, column_offset, batch_size, feature_size, false, as_stream(stream));
+}
+
+int nts_scatter_grad_back_to_message(const float *input, float *message_grad, const nts_vid_t *row_indices,
+                                     const nts_vid_t *column_offset, nts_vid_t batch_size, nts_vid_t feature_size,
+                                     void *stream) {
+  (void)row_indices;
+  return segment_broadcast(message_grad, input, column_offset, batch_size, feature_size, true, as_stream(stream));
+}
+
+int nts_gather_msg_to_dst(float *dst_feature, const float *message, const nts_vid_t *row_indices,
+                          const nts_vid_t *column_offset, nts_vid_t batch_size, nts_vid_t feature_size,
+                          void *stream) {
+  (void)row_indices;
+  cudaStream_t st = as_stream(stream);
+  if (batch_size == 0 || feature_size == 0)
+    return 0;
+  NTS_ARG_CHECK(dst_feature && message && column_offset, "null pointer passed to gather_msg_to_dst");
+  int vec = pick_vec(feature_size, dst_feature, message);
+  unsigned grid = full_grid();
+  if (vec == 4)
+    segment_sum_kernel<4><<<grid, kThreads, 0, st>>>(dst_feature, message, column_offset, batch_size, feature_size);
+  else if (vec == 2)
+    segment_sum_kernel<2><<<grid, kThreads, 0, st>>>(dst_feature, message, column_offset, batch_size, feature_size);
+  else
+    segment_sum_kernel<1><<<grid, kThreads, 0, st>>>(dst_feature, message, column_offset, batch_size, feature_size);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_edge_softmax_forward(float *msg_output, const float *msg_input, float *msg_cached,
+                             const nts_vid_t *row_indices, const nts_vid_t *column_offset, nts_vid_t batch_size,
+                             nts_vid_t feature_size, void *stream) {
+  (void)row_indices;
+  if (batch_size == 0 || feature_size == 0)
+    return 0;
+  NTS_ARG_CHECK(msg_output && msg_input && column_offset, "null pointer passed to edge softmax");
+  unsigned grid = (batch_size + kRowsPerCta - 1) / kRowsPerCta;
+  edge_softmax_kernel<false><<<grid, kThreads, 0, as_stream(stream)>>>(msg_output, msg_input, nullptr, msg_cached,
+                                                                       column_offset, batch_size, feature_size);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_edge_softmax_backward(float *msg_input_grad, const float *msg_output_grad, const float *msg_cached,
+                              const nts_vid_t *row_indices, const nts_vid_t *column_offset, nts_vid_t batch_size,
+                              nts_vid_t feature_size, void *stream) {
+  (void)row_indices;
+  if (batch_size == 0 || feature_size == 0)
+    return 0;
+  NTS_ARG_CHECK(msg_input_grad && msg_output_grad && msg_cached && column_offset,
+                "null pointer passed to edge softmax backward");
+  unsigned grid = (batch_size + kRowsPerCta - 1) / kRowsPerCta;
+  edge_softmax_kernel<true><<<grid, kThreads, 0, as_stream(stream)>>>(msg_input_grad, msg_output_grad, msg_cached,
+                                                                      nullptr, column_offset, batch_size,
+                                                                      feature_size);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_aggregate_dst_fuse_weight_backward(float *mirror_grad, float *edge_weight_grad, const float *mirror,
+                                           const float *edge_weight, const float *dst_grad,
+                                           const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                           const nts_vid_t *mirror_index, nts_vid_t batch_size,
+                                           nts_vid_t feature_size, void *stream) {
+  cudaStream_t st = as_stream(stream);
+  if (batch_size == 0 || feature_size == 0)
+    return 0;
+  NTS_ARG_CHECK(mirror_grad && edge_weight_grad && mirror && edge_weight && dst_grad && row_indices &&
+                    column_offset && mirror_index,
+                "null pointer passed to fuse-weight backward");
+  int vec = pick_vec(feature_size, mirror_grad, mirror, dst_grad);
+  unsigned grid = full_grid();
+  if (vec == 4)
+    fuse_weight_backward_kernel<4><<<grid, kThreads, 0, st>>>(mirror_grad, edge_weight_grad, mirror, edge_weight,
+                                                              dst_grad, row_indices, column_offset, mirror_index,
+                                                              batch_size, feature_size);
+  else if (vec == 2)
+    fuse_weight_backward_kernel<2><<<grid, kThreads, 0, st>>>(mirror_grad, edge_weight_grad, mirror, edge_weight,
+                                                              dst_grad, row_indices, column_offset, mirror_index,
+                                                              batch_size, feature_size);
+  else
+    fuse_weight_backward_kernel<1><<<grid, kThreads, 0, st>>>(mirror_grad, edge_weight_grad, mirror, edge_weight,
+                                                              dst_grad, row_indices, column_offset, mirror_index,
+                                                              batch_size, feature_size);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_deserialize_records(float *mirror, const float *records, nts_vid_t n_records, nts_vid_t feature_size,
+                            nts_vid_t partition_start, nts_vid_t partition_end, void *stream) {
+  if (n_records == 0)
+    return 0;
+  NTS_ARG_CHECK(mirror && records, "null pointer passed to deserialize_records");
+  records_kernel<false><<<stream_grid(n_records), kThreads, 0, as_stream(stream)>>>(
+      mirror, records, n_records, feature_size, partition_start, partition_end);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_aggregate_records(float *aggregate, const float *records, nts_vid_t n_records, nts_vid_t feature_size,
+                          nts_vid_t partition_start, nts_vid_t partition_end, void *stream) {
+  if (n_records == 0)
+    return 0;
+  NTS_ARG_CHECK(aggregate && records, "null pointer passed to aggregate_records");
+  records_kernel<true><<<stream_grid(n_records), kThreads, 0, as_stream(stream)>>>(
+      aggregate, records, n_records, feature_size, partition_start, partition_end);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,241 @@
+"""Graph operators with the reference's `ntsGraphOp` interface (core/ntsBaseOp.hpp:24-48):
+constructed from `(PartitionedGraph, active)`, `forward(x)` / `forward(x, w)`, `backward(grad)`,
+`get_additional_grad()`; outputs are freshly allocated zero tensors the kernels accumulate into
+(NtsScheduler::NewKeyTensor / NewLeafTensor, core/NtsScheduler.hpp:378-394).
+
+Every operator calls the sm_100a kernels through the C ABI (`_lib.call`); tensors only provide device
+memory and the current CUDA stream.  There is no CPU path: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_input(t, name="input"):
+    if not t.is_cuda:
+        raise _lib.NtsError("%s must be a CUDA tensor (libnts_b200 has no CPU fallback)" % name)
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise _lib.NtsError("%s must be a 2-D float32 tensor" % name)
+    if not t.is_contiguous():
+        # the reference borrows packed_accessor storage (core/NtsScheduler.hpp:505-515): contiguous only
+        raise _lib.NtsError("%s must be contiguous" % name)
+    return t
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def segment_gather_sum(out, x, weight, indices, offsets, index_base, n_rows, n_edges):
+    """out[r,:] += sum_e x[indices[e]-index_base,:] * weight[e]  (nts_segment_gather_sum)."""
+    _lib.call("nts_segment_gather_sum", _ptr(x), _ptr(out), _ptr(weight), _ptr(indices), _ptr(offsets),
+              int(index_base), int(n_rows), int(n_edges), int(x.shape[1]), _stream())
+    return out
+
+
+def gather_by_dst_from_src(chunk, out, x, with_weight=True):
+    """NtsScheduler::GatherByDstFromSrc (core/NtsScheduler.hpp:151-191) on one chunk."""
+    _lib.call("nts_gather_by_dst_from_src", _ptr(x), _ptr(out), _ptr(chunk.edge_weight_forward_gpu),
+              _ptr(chunk.row_indices_gpu), _ptr(chunk.column_offset_gpu), chunk.src_range[0], chunk.src_range[1],
+              chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_forward,
+              int(x.shape[1]), 1 if with_weight else 0, _stream())
+    return out
+
+
+def gather_by_src_from_dst(chunk, out, grad, with_weight=True):
+    """NtsScheduler::GatherBySrcFromDst (core/NtsScheduler.hpp:257-293) on one chunk."""
+    _lib.call("nts_gather_by_src_from_dst", _ptr(grad), _ptr(out), _ptr(chunk.edge_weight_backward_gpu),
+              _ptr(chunk.row_offset_gpu), _ptr(chunk.column_indices_gpu), chunk.src_range[0], chunk.src_range[1],
+              chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_backward,
+              int(grad.shape[1]), 1 if with_weight else 0, _stream())
+    return out
+
+
+class ntsGraphOp:
+    """core/ntsBaseOp.hpp:24-48."""
+
+    def __init__(self, partitioned_graph, active=None):
+        self.partitioned_graph_ = partitioned_graph
+        self.active_ = active
+
+    def forward(self, f_input, f_input1=None):
+        raise NotImplementedError
+
+    def backward(self, output_grad):
+        raise NotImplementedError
+
+    def get_additional_grad(self):
+        raise NotImplementedError("get_additional_grad is not implemented")
+
+
+class ForwardSingleGPUfuseOp(ntsGraphOp):
+    """core/ntsSingleGPUFusedGraphOp.hpp:48-71 -> Graph::forward_single / backward_single
+    (core/graph.hpp:3805-3855): Y = A X on chunk 0, dX = A^T dY, no communication."""
+
+    def forward(self, f_input, f_input1=None):
+        x = _check_input(f_input)
+        c = self.partitioned_graph_.graph_chunks[0]
+        y = torch.zeros((c.batch_size_forward, x.shape[1]), dtype=torch.float32, device=x.device)
+        return gather_by_dst_from_src(c, y, x)
+
+    def backward(self, f_output_grad):
+        g = _check_input(f_output_grad, "output_grad")
+        c = self.partitioned_graph_.graph_chunks[0]
+        dx = torch.zeros((c.batch_size_backward, g.shape[1]), dtype=torch.float32, device=g.device)
+        return gather_by_src_from_dst(c, dx, g)
+
+
+class ForwardGPUfuseOp(ntsGraphOp):
+    """core/ntsDistGPUFusedGraphOp.hpp:48-90: the distributed fused GCN aggregation.  The reference drives it
+    through Graph::sync_compute_decoupled / compute_sync_decoupled with host-staged MPI messages
+    (core/graph.hpp:3455-3719); here the exchange is device-resident (neutronstarlite_b200.exchange)."""
+
+    def __init__(self, partitioned_graph, active=None, exchange=None):
+        super().__init__(partitioned_graph, active)
+        if exchange is None:
+            from .exchange import default_exchange
+            exchange = default_exchange(partitioned_graph)
+        self.exchange = exchange
+
+    def forward(self, f_input, f_input1=None):
+        return self.exchange.forward(_check_input(f_input))
+
+    def backward(self, f_output_grad):
+        return self.exchange.backward(_check_input(f_output_grad, "output_grad"))
+
+
+# ---- edge-granular operators (core/ntsDistGPUGraphOp.hpp) ------------------------------------------------------
+class _EdgeOp(ntsGraphOp):
+    def _topo(self):
+        pg = self.partitioned_graph_
+        if pg.column_offset_gpu is None or pg.row_indices_gpu is None:
+            raise _lib.NtsError("whole-partition CSC missing: call PartitionedGraph.generate_all(dist=True, device=...)")
+        return pg
+
+
+class DistGPUScatterSrc(_EdgeOp):
+    """core/ntsDistGPUGraphOp.hpp:100-176: mirror [M,F] -> edge messages [E_p,F]."""
+
+    def forward(self, f_input, f_input1=None):
+        pg = self._topo()
+        x = _check_input(f_input)
+        msg = torch.zeros((pg.owned_edges, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.call("nts_scatter_src_mirror_to_msg", _ptr(msg), _ptr(x), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, x.shape[1], _stream())
+        return msg
+
+    def backward(self, f_output_grad):
+        pg = self._topo()
+        g = _check_input(f_output_grad, "output_grad")
+        out = torch.zeros((pg.owned_mirrors, g.shape[1]), dtype=torch.float32, device=g.device)
+        _lib.call("nts_gather_msg_to_src_mirror", _ptr(out), _ptr(g), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, g.shape[1], _stream())
+        return out
+
+
+class DistGPUScatterDst(_EdgeOp):
+    """core/ntsDistGPUGraphOp.hpp:178-238: local vertices [V_p,F] -> edge messages [E_p,F]."""
+
+    def forward(self, f_input, f_input1=None):
+        pg = self._topo()
+        x = _check_input(f_input)
+        msg = torch.zeros((pg.owned_edges, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.call("nts_scatter_dst_to_msg", _ptr(msg), _ptr(x), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), pg.owned_vertices, x.shape[1], _stream())
+        return msg
+
+    def backward(self, f_output_grad):
+        pg = self._topo()
+        g = _check_input(f_output_grad, "output_grad")
+        out = torch.zeros((pg.owned_vertices, g.shape[1]), dtype=torch.float32, device=g.device)
+        _lib.call("nts_gather_msg_to_dst", _ptr(out), _ptr(g), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), pg.owned_vertices, g.shape[1], _stream())
+        return out
+
+
+class DistGPUAggregateDst(_EdgeOp):
+    """core/ntsDistGPUGraphOp.hpp:240-300: edge messages [E_p,F] -> sum per destination [V_p,F]."""
+
+    def forward(self, f_input, f_input1=None):
+        pg = self._topo()
+        m = _check_input(f_input)
+        out = torch.zeros((pg.owned_vertices, m.shape[1]), dtype=torch.float32, device=m.device)
+        _lib.call("nts_gather_msg_to_dst", _ptr(out), _ptr(m), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), pg.owned_vertices, m.shape[1], _stream())
+        return out
+
+    def backward(self, f_output_grad):
+        pg = self._topo()
+        g = _check_input(f_output_grad, "output_grad")
+        msg = torch.zeros((pg.owned_edges, g.shape[1]), dtype=torch.float32, device=g.device)
+        _lib.call("nts_scatter_dst_to_msg", _ptr(msg), _ptr(g), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), pg.owned_vertices, g.shape[1], _stream())
+        return msg
+
+
+class DistGPUEdgeSoftMax(_EdgeOp):
+    """core/ntsDistGPUGraphOp.hpp:302-361; numerics follow the CPU operator DistEdgeSoftMax
+    (core/ntsDistCPUGraphOp.hpp:442-492): column-wise, max-subtracted."""
+
+    def __init__(self, partitioned_graph, active=None):
+        super().__init__(partitioned_graph, active)
+        self.IntermediateResult = None
+
+    def forward(self, f_input, f_input1=None):
+        pg = self._topo()
+        m = _check_input(f_input)
+        out = torch.zeros_like(m)
+        self.IntermediateResult = torch.zeros_like(m)
+        _lib.call("nts_edge_softmax_forward", _ptr(out), _ptr(m), _ptr(self.IntermediateResult),
+                  _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu), pg.owned_vertices, m.shape[1], _stream())
+        return out
+
+    def backward(self, f_output_grad):
+        pg = self._topo()
+        g = _check_input(f_output_grad, "output_grad")
+        out = torch.zeros_like(g)
+        _lib.call("nts_edge_softmax_backward", _ptr(out), _ptr(g), _ptr(self.IntermediateResult),
+                  _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu), pg.owned_vertices, g.shape[1], _stream())
+        return out
+
+
+class DistGPUAggregateDstFuseWeight(_EdgeOp):
+    """GPU twin of DistAggregateDstFuseWeight (core/ntsDistCPUGraphOp.hpp:499-594), the fused GAT aggregation
+    of toolkits/GAT_CPU_DIST_OPTM.hpp:196-241: y[d,:] = sum_e a[e] * mirror[MirrorIndex[src(e)],:], never
+    materialising an [E,F] message.  backward returns d_mirror; `get_additional_grad()` returns d_a [E,1]."""
+
+    def __init__(self, partitioned_graph, active=None):
+        super().__init__(partitioned_graph, active)
+        self._mirror = None
+        self._a = None
+        self.e_weight_grad = None
+
+    def forward(self, f_input, e_weight=None):
+        pg = self._topo()
+        x = _check_input(f_input)
+        a = _check_input(e_weight, "edge weight")
+        self._mirror, self._a = x, a
+        out = torch.zeros((pg.owned_vertices, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.call("nts_segment_gather_sum_slots", _ptr(x), _ptr(out), _ptr(a), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, pg.owned_edges,
+                  x.shape[1], _stream())
+        return out
+
+    def backward(self, f_output_grad):
+        pg = self._topo()
+        g = _check_input(f_output_grad, "output_grad")
+        dm = torch.zeros((pg.owned_mirrors, g.shape[1]), dtype=torch.float32, device=g.device)
+        self.e_weight_grad = torch.zeros_like(self._a)
+        _lib.call("nts_aggregate_dst_fuse_weight_backward", _ptr(dm), _ptr(self.e_weight_grad), _ptr(self._mirror),
+                  _ptr(self._a), _ptr(g), _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu),
+                  _ptr(pg.mirror_index_gpu), pg.owned_vertices, g.shape[1], _stream())
+        return dm
+
+    def get_additional_grad(self):
+        return self.e_weight_grad

@@ -1,0 +1,48 @@
+"""CPU-only checks of the drop-in boundary: the shared object loads and exports every symbol that
+include/nts_b200.h declares, the ctypes table covers the header, and the product has no CPU fallback."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from neutronstarlite_b200 import _lib
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _lib.header_symbols()
+    assert len(declared) >= 50
+    for name in declared:
+        assert hasattr(lib, name), "libnts_b200.so does not export %s" % name
+    assert lib.nts_version() == 1
+
+
+def test_ctypes_table_matches_header():
+    assert sorted(_lib.SIGNATURES) == _lib.header_symbols()
+
+
+def test_product_does_not_import_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "neutronstarlite_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "nts_oracle" not in text, "%s references the oracle" % f
+                assert "oracle/" not in text, "%s references the oracle directory" % f
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from neutronstarlite_b200 import ops
+    with pytest.raises(_lib.NtsError):
+        ops._check_input(torch.zeros(4, 4))
+
+
+def test_argument_errors_are_reported_not_swallowed():
+    lib = _lib.load()
+    rc = lib.nts_aggregate_set_variant(7, 0)
+    assert rc != 0
+    assert b"variant" in lib.nts_last_error()
+    assert lib.nts_aggregate_set_variant(0, 0) == 0

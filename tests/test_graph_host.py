@@ -1,0 +1,65 @@
+"""Host-side layout (nts_graph_host.cpp through the C ABI) against the golden artefacts dumped by the unmodified
+reference at P = 1, 2, 4, 8: partition offsets, degrees, every chunk's CSC/CSR arrays and weights, MirrorIndex and
+the whole-partition CSC - all bit-exact (CSR rows as multisets: their order is a race in the reference)."""
+import numpy as np
+
+from neutronstarlite_b200.graph import HostGraph, PartitionedGraph
+
+
+def rows_as_multisets(offsets, idx):
+    out = idx.copy()
+    off = offsets.astype(np.int64)
+    for r in range(off.shape[0] - 1):
+        out[off[r]:off[r + 1]] = np.sort(out[off[r]:off[r + 1]])
+    return out
+
+
+def test_degrees_partition_offsets(golden):
+    g = golden
+    hg = HostGraph(g.edges, g.V)
+    out_d, in_d = hg.degrees()
+    assert np.array_equal(out_d, g.get(0, "out_degree"))
+    assert np.array_equal(in_d, g.get(0, "in_degree"))
+    assert np.array_equal(hg.partition_offsets(g.P), g.partition_offset)
+
+
+def test_chunks_mirror_index_whole_topo(golden):
+    g = golden
+    hg = HostGraph(g.edges, g.V)
+    for r in range(g.P):
+        pg = PartitionedGraph(hg, g.P, r).generate_all(dist=True)
+        assert pg.owned_vertices == int(g.get(r, "meta")[4])
+        assert pg.owned_edges == int(g.get(r, "meta")[5])
+        assert pg.owned_mirrors == int(g.get(r, "meta")[6])
+        for i, c in enumerate(pg.graph_chunks):
+            t = "chunk%d_" % i
+            meta = g.get(r, t + "meta")
+            assert (meta[0], meta[1], meta[2]) == (c.edge_size, c.batch_size_forward, c.batch_size_backward)
+            assert (meta[3], meta[4]) == c.src_range and (meta[5], meta[6]) == c.dst_range
+            assert np.array_equal(c.column_offset, g.get(r, t + "column_offset"))
+            assert np.array_equal(c.row_indices, g.get(r, t + "row_indices"))
+            assert np.array_equal(c.edge_weight_forward.view(np.uint32),
+                                  g.get(r, t + "edge_weight_forward").view(np.uint32))
+            assert np.array_equal(c.row_offset, g.get(r, t + "row_offset"))
+            ref_ci = g.get(r, t + "column_indices")
+            assert np.array_equal(c.column_indices, rows_as_multisets(c.row_offset, ref_ci))
+            # backward weights: compare as per-row multisets of (dst, weight-bits) pairs
+            ref_w = g.get(r, t + "edge_weight_backward").view(np.uint32).astype(np.uint64)
+            mine_w = c.edge_weight_backward.view(np.uint32).astype(np.uint64)
+            ref_pairs = (ref_ci.astype(np.uint64) << np.uint64(32)) | ref_w
+            my_pairs = (c.column_indices.astype(np.uint64) << np.uint64(32)) | mine_w
+            assert np.array_equal(rows_as_multisets(c.row_offset, my_pairs),
+                                  rows_as_multisets(c.row_offset, ref_pairs))
+            assert np.array_equal(c.source_active, g.get(r, t + "source_active"))
+        assert np.array_equal(pg.MirrorIndex, g.get(r, "mirror_index"))
+        assert np.array_equal(pg.column_offset, g.get(r, "whole_column_offset"))
+        assert np.array_equal(pg.row_indices, g.get(r, "whole_row_indices"))
+
+
+def test_empty_graph_and_single_vertex():
+    hg = HostGraph(np.zeros((0, 2), dtype=np.uint32), 5)
+    pg = PartitionedGraph(hg, 1, 0).generate_all(dist=True)
+    assert pg.owned_edges == 0 and pg.owned_mirrors == 0
+    assert np.array_equal(pg.graph_chunks[0].column_offset, np.zeros(6, dtype=np.uint32))
+    out_d, in_d = hg.degrees()
+    assert (out_d == 1).all() and (in_d == 1).all()

@@ -14,6 +14,12 @@ def close(a, b):
     np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL)
 
 
+def close_acc(a, b):
+    """For results the reference accumulates with `nts_acc` (CAS float add from OMP threads,
+    core/ntsBaseOp.hpp:114-126): its own summation order is a race, so allow re-association noise."""
+    np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5)
+
+
 def rows_as_multisets(offsets, idx):
     out = idx.copy()
     off = offsets.astype(np.int64)
@@ -98,7 +104,7 @@ def test_gcn_forward_backward(golden):
     X = _global(g, "X")
     G = _global(g, "G")
     close(O.gcn_forward_all(g.edges, g.V, g.P, X), _global(g, "gcn_Y"))
-    close(O.gcn_backward_all(g.edges, g.V, g.P, G), _global(g, "gcn_dX"))
+    close_acc(O.gcn_backward_all(g.edges, g.V, g.P, G), _global(g, "gcn_dX"))
 
 
 def test_partition_invariance(golden):
@@ -126,9 +132,9 @@ def test_edge_ops(golden):
             assert np.array_equal(O.scatter_src_mirror_to_msg(co, ri, mi, mirror), g.mat(r, "scatter_src_msg"))
             assert np.array_equal(O.scatter_dst_to_msg(co, Xl), g.mat(r, "scatter_dst_msg"))
             assert np.array_equal(O.scatter_dst_to_msg(co, Gl), g.mat(r, "aggregate_dst_dmsg"))
-        close(O.gather_msg_to_src_mirror(co, ri, mi, Ge, M), g.mat(r, "scatter_src_dmirror"))
-        close(O.gather_msg_to_dst(co, Ge), g.mat(r, "scatter_dst_dX"))
-        close(O.gather_msg_to_dst(co, Ge), g.mat(r, "aggregate_dst_Y"))
+        close_acc(O.gather_msg_to_src_mirror(co, ri, mi, Ge, M), g.mat(r, "scatter_src_dmirror"))
+        close_acc(O.gather_msg_to_dst(co, Ge), g.mat(r, "scatter_dst_dX"))
+        close_acc(O.gather_msg_to_dst(co, Ge), g.mat(r, "aggregate_dst_Y"))
         a = O.edge_softmax_forward(co, g.mat(r, "softmax_in", 1))
         close(a, g.mat(r, "softmax_out", 1))
         close(O.edge_softmax_backward(co, g.mat(r, "softmax_out", 1), g.mat(r, "softmax_gout", 1)),
