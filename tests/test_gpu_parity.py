@@ -1,0 +1,352 @@
+"""Parity of the sm_100a kernels, called through the C ABI, against
+  (1) the golden vectors of the UNMODIFIED reference CPU operators (tests/golden, P = 1, 2, 4, 8),
+  (2) the C / numpy oracle on seeded random multigraphs (hubs, empty rows, duplicates; every vector-width class),
+  (3) size-independent properties at larger sizes (exact in-degree counts, linearity).
+Tolerance for float results: 1e-4 relative (BASELINE.json north_star), written as RTOL below; integer-valued
+results (copies, counts) must be bit-exact."""
+import numpy as np
+import pytest
+
+import nts_oracle as O
+import oracle_c
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+ATOL = 1e-5
+
+
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def up(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.view(dtype) if t.element_size() == torch.tensor([], dtype=dtype).element_size() else t.to(dtype)
+    return t.to(dev())
+
+
+def up_u32(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32)).to(dev())
+
+
+def close(actual, desired, rtol=RTOL, atol=ATOL):
+    scale = max(1.0, float(np.abs(desired).max()) if desired.size else 1.0)
+    np.testing.assert_allclose(actual, desired, rtol=rtol, atol=atol * scale)
+
+
+def lib():
+    from neutronstarlite_b200 import _lib
+    return _lib
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def gpu_segment_gather(offsets, indices, w, X, base, out=None, slots=None):
+    L = lib()
+    n_rows = offsets.shape[0] - 1
+    d_off, d_idx = up_u32(offsets), up_u32(indices)
+    d_w = None if w is None else up(w.astype(np.float32))
+    d_x = up(X.astype(np.float32))
+    d_out = torch.zeros((n_rows, X.shape[1]), dtype=torch.float32, device=dev()) if out is None else up(out)
+    if slots is None:
+        L.call("nts_segment_gather_sum", d_x.data_ptr(), d_out.data_ptr(), 0 if d_w is None else d_w.data_ptr(),
+               d_idx.data_ptr(), d_off.data_ptr(), int(base), n_rows, int(indices.shape[0]), X.shape[1], stream())
+    else:
+        d_s = up_u32(slots)
+        L.call("nts_segment_gather_sum_slots", d_x.data_ptr(), d_out.data_ptr(), 0 if d_w is None else d_w.data_ptr(),
+               d_idx.data_ptr(), d_off.data_ptr(), d_s.data_ptr(), n_rows, int(indices.shape[0]), X.shape[1], stream())
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (1) golden vectors of the reference
+# ------------------------------------------------------------------------------------------------------------
+def test_golden_gcn_forward_backward_per_rank(golden):
+    """Each rank's chunks exactly as the reference built them (its own arrays), run chunk after chunk in the
+    reference's ring order through nts_gather_by_dst_from_src / nts_gather_by_src_from_dst."""
+    from neutronstarlite_b200 import ops
+    from neutronstarlite_b200.graph import CSCSegment
+    g = golden
+    po = g.partition_offset
+    Xg = np.concatenate([g.mat(r, "X") for r in range(g.P)], axis=0)
+    dX_acc = np.zeros((g.V, g.F), dtype=np.float32)
+    for r in range(g.P):
+        Vp = int(po[r + 1] - po[r])
+        y = torch.zeros((Vp, g.F), dtype=torch.float32, device=dev())
+        G = up(g.mat(r, "G"))
+        for step in range(g.P):
+            i = (r + step) % g.P
+            t = "chunk%d_" % i
+            c = CSCSegment()
+            meta = g.get(r, t + "meta")
+            c.edge_size, c.batch_size_forward, c.batch_size_backward = int(meta[0]), int(meta[1]), int(meta[2])
+            c.src_range, c.dst_range = (int(meta[3]), int(meta[4])), (int(meta[5]), int(meta[6]))
+            for name in ("column_offset", "row_indices", "row_offset", "column_indices"):
+                setattr(c, name + "_gpu", up_u32(g.get(r, t + name)))
+            c.edge_weight_forward_gpu = up(g.get(r, t + "edge_weight_forward"))
+            c.edge_weight_backward_gpu = up(g.get(r, t + "edge_weight_backward"))
+            xs = up(Xg[c.src_range[0]:c.src_range[1]])
+            if xs.shape[0] and Vp:
+                ops.gather_by_dst_from_src(c, y, xs)
+            if c.batch_size_backward and Vp:
+                part = torch.zeros((c.batch_size_backward, g.F), dtype=torch.float32, device=dev())
+                ops.gather_by_src_from_dst(c, part, G)
+                dX_acc[c.src_range[0]:c.src_range[1]] += part.cpu().numpy()
+        close(y.cpu().numpy(), g.mat(r, "gcn_Y"))
+    ref_dX = np.concatenate([g.mat(r, "gcn_dX") for r in range(g.P)], axis=0)
+    close(dX_acc, ref_dX)
+
+
+def test_golden_edge_ops(golden):
+    from neutronstarlite_b200 import ops
+    from neutronstarlite_b200.graph import PartitionedGraph
+    g = golden
+    po = g.partition_offset
+    for r in range(g.P):
+        Vp, Ep, M = (int(x) for x in g.get(r, "meta")[4:7])
+        if Vp == 0:
+            continue
+        pg = PartitionedGraph(None, g.P, r, po)
+        pg.owned_vertices, pg.owned_edges, pg.owned_mirrors = Vp, Ep, M
+        pg.column_offset_gpu = up_u32(g.get(r, "whole_column_offset"))
+        pg.row_indices_gpu = up_u32(g.get(r, "whole_row_indices"))
+        pg.mirror_index_gpu = up_u32(g.get(r, "mirror_index"))
+        mirror = up(g.mat(r, "dep_mirror"))
+        X = up(g.mat(r, "X"))
+        G = up(g.mat(r, "G"))
+        Ge = up(g.mat(r, "Ge"))
+        # copies: bit-exact
+        op = ops.DistGPUScatterSrc(pg)
+        msg = op.forward(mirror).cpu().numpy()
+        assert np.array_equal(msg, g.mat(r, "dep_mirror")[g.get(r, "mirror_index")[g.get(r, "whole_row_indices")]])
+        if g.has(r, "scatter_src_msg"):
+            assert np.array_equal(msg, g.mat(r, "scatter_src_msg"))
+        close(op.backward(Ge).cpu().numpy(), g.mat(r, "scatter_src_dmirror"))
+        op = ops.DistGPUScatterDst(pg)
+        msg = op.forward(X).cpu().numpy()
+        if g.has(r, "scatter_dst_msg"):
+            assert np.array_equal(msg, g.mat(r, "scatter_dst_msg"))
+        close(op.backward(Ge).cpu().numpy(), g.mat(r, "scatter_dst_dX"))
+        op = ops.DistGPUAggregateDst(pg)
+        close(op.forward(Ge).cpu().numpy(), g.mat(r, "aggregate_dst_Y"))
+        dmsg = op.backward(G).cpu().numpy()
+        if g.has(r, "aggregate_dst_dmsg"):
+            assert np.array_equal(dmsg, g.mat(r, "aggregate_dst_dmsg"))
+        # softmax: reference tolerance is 1e-7 on a constant input (test_getdepneighbor_gpu.hpp:316); we use 1e-5 abs
+        op = ops.DistGPUEdgeSoftMax(pg)
+        a = op.forward(up(g.mat(r, "softmax_in", 1)))
+        np.testing.assert_allclose(a.cpu().numpy(), g.mat(r, "softmax_out", 1), rtol=RTOL, atol=1e-6)
+        gin = op.backward(up(g.mat(r, "softmax_gout", 1)))
+        np.testing.assert_allclose(gin.cpu().numpy(), g.mat(r, "softmax_gin", 1), rtol=RTOL, atol=1e-5)
+        # fused aggregation
+        op = ops.DistGPUAggregateDstFuseWeight(pg)
+        att = up(g.mat(r, "softmax_out", 1))
+        close(op.forward(mirror, att).cpu().numpy(), g.mat(r, "fuse_Y"))
+        dm = op.backward(G).cpu().numpy()
+        dw = op.get_additional_grad().cpu().numpy()
+        close(dw, g.mat(r, "fuse_dweight", 1))
+        # the reference adds the unweighted gradient once more (core/ntsDistCPUGraphOp.hpp:572) and races; compare
+        # with the oracle restatement of the correct gradient instead
+        co, ri, mi = g.get(r, "whole_column_offset"), g.get(r, "whole_row_indices"), g.get(r, "mirror_index")
+        dm_o, dw_o = O.aggregate_dst_fuse_weight_backward(co, ri, mi, g.mat(r, "dep_mirror"),
+                                                          g.mat(r, "softmax_out", 1), g.mat(r, "G"), M)
+        close(dm, dm_o)
+        close(dw, dw_o)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (2) seeded random multigraphs against the C oracle
+# ------------------------------------------------------------------------------------------------------------
+def random_csr(n_rows, n_src, n_edges, seed, hub_rows=2, empty_every=7):
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, n_rows, n_edges)
+    rows[rows % empty_every == 3] = (rows[rows % empty_every == 3] + 1) % n_rows  # leave some rows empty
+    for h in range(hub_rows):
+        rows[rng.integers(0, n_edges, n_edges // 6)] = (h * 31 + 5) % n_rows      # hubs cut by many quanta
+    rows.sort()
+    idx = rng.integers(0, n_src, n_edges).astype(np.uint32)
+    off = np.zeros(n_rows + 1, dtype=np.uint32)
+    np.cumsum(np.bincount(rows, minlength=n_rows), out=off[1:])
+    w = rng.uniform(-1, 1, n_edges).astype(np.float32)
+    return off, idx, w
+
+
+@pytest.mark.parametrize("F", [1, 2, 7, 41, 47, 64, 100, 128, 172, 256, 602, 1433])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_random_graph_vs_c_oracle(F, variant):
+    """Every vector-width / chunk-count class of the kernel, both index-staging variants, accumulate-into-output
+    semantics and a non-zero index base (global source ids of a remote partition)."""
+    L = lib()
+    off, idx, w = random_csr(1500, 1100, 40000, seed=F * 13 + variant)
+    rng = np.random.default_rng(F)
+    X = rng.uniform(-1, 1, (1100, F)).astype(np.float32)
+    init = rng.uniform(-1, 1, (1500, F)).astype(np.float32)  # kernels ACCUMULATE into the output
+    base = 4096
+    try:
+        L.call("nts_aggregate_set_variant", variant, 0)
+        got0 = gpu_segment_gather(off, idx, w, X, 0, out=init)
+        got1 = gpu_segment_gather(off, idx + base, w, X, base, out=init)
+    finally:
+        L.call("nts_aggregate_set_variant", 0, 0)
+    ref = oracle_c.segment_gather_sum(off, idx, w, X, base=0, out=init.copy())
+    close(got0, ref)
+    close(got1, ref)
+
+
+@pytest.mark.parametrize("Q", [32, 64, 512])
+def test_quantum_sizes_and_unweighted(Q):
+    L = lib()
+    off, idx, w = random_csr(700, 900, 30000, seed=Q)
+    X = np.random.default_rng(Q).uniform(-1, 1, (900, 96)).astype(np.float32)
+    try:
+        for variant in (1, 2):
+            L.call("nts_aggregate_set_variant", variant, Q)
+            close(gpu_segment_gather(off, idx, None, X, 0), oracle_c.segment_gather_sum(off, idx, None, X))
+            close(gpu_segment_gather(off, idx, w, X, 0), oracle_c.segment_gather_sum(off, idx, w, X))
+    finally:
+        L.call("nts_aggregate_set_variant", 0, 0)
+
+
+def test_slot_table_variant():
+    off, idx, w = random_csr(300, 5000, 9000, seed=5)
+    rng = np.random.default_rng(9)
+    used = np.unique(idx)
+    slot_of = np.zeros(5000, dtype=np.uint32)
+    slot_of[used] = rng.permutation(used.shape[0]).astype(np.uint32)
+    Xc = rng.uniform(-1, 1, (used.shape[0], 64)).astype(np.float32)
+    ref = oracle_c.segment_gather_sum(off, slot_of[idx], w, Xc)
+    close(gpu_segment_gather(off, idx, w, Xc, 0, slots=slot_of), ref)
+
+
+def test_empty_and_degenerate_inputs():
+    L = lib()
+    # no edges at all: the output must be untouched
+    off = np.zeros(11, dtype=np.uint32)
+    out = gpu_segment_gather(off, np.zeros(0, dtype=np.uint32), None, np.ones((4, 8), np.float32), 0,
+                             out=np.full((10, 8), 3.0, np.float32))
+    assert (out == 3.0).all()
+    # one row owning every edge (a pure hub), one edge, leading/trailing empty rows
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, 50, 5000).astype(np.uint32)
+    w = rng.uniform(-1, 1, 5000).astype(np.float32)
+    X = rng.uniform(-1, 1, (50, 602)).astype(np.float32)
+    off = np.array([0, 0, 0, 5000, 5000], dtype=np.uint32)
+    close(gpu_segment_gather(off, idx, w, X, 0), oracle_c.segment_gather_sum(off, idx, w, X))
+    off = np.array([0, 0, 1, 1], dtype=np.uint32)
+    close(gpu_segment_gather(off, idx[:1], w[:1], X, 0), oracle_c.segment_gather_sum(off, idx[:1], w[:1], X))
+
+
+def test_gather_scatter_rows_and_records():
+    L = lib()
+    rng = np.random.default_rng(3)
+    src = rng.uniform(-1, 1, (500, 602)).astype(np.float32)
+    rows = rng.permutation(500)[:200].astype(np.uint32)
+    d_src, d_rows = up(src), up_u32(rows)
+    d_dst = torch.zeros((200, 602), dtype=torch.float32, device=dev())
+    L.call("nts_gather_rows", d_dst.data_ptr(), d_src.data_ptr(), d_rows.data_ptr(), 200, 602, stream())
+    assert np.array_equal(d_dst.cpu().numpy(), src[rows])
+    acc = rng.uniform(-1, 1, (500, 602)).astype(np.float32)
+    d_acc = up(acc)
+    L.call("nts_scatter_add_rows", d_acc.data_ptr(), d_dst.data_ptr(), d_rows.data_ptr(), 200, 602, stream())
+    expect = acc.copy()
+    expect[rows] += src[rows]
+    assert np.array_equal(d_acc.cpu().numpy(), expect)
+    # (vid,row) records through mapped pinned memory, the reference's message format
+    F, n = 16, 300
+    rec = np.zeros((n, F + 1), dtype=np.float32)
+    vids = rng.permutation(1000)[:n].astype(np.uint32)
+    rec[:, 0] = vids.view(np.float32)
+    rec[:, 1:] = rng.uniform(-1, 1, (n, F)).astype(np.float32)
+    hp = L.load().nts_malloc_pinned(rec.nbytes)
+    import ctypes
+    ctypes.memmove(hp, rec.ctypes.data, rec.nbytes)
+    dp = L.load().nts_pinned_device_pointer(hp)
+    mirror = torch.zeros((400, F), dtype=torch.float32, device=dev())
+    L.call("nts_deserialize_records", mirror.data_ptr(), dp, n, F, 100, 500, stream())
+    torch.cuda.synchronize()
+    expect = np.zeros((400, F), dtype=np.float32)
+    sel = (vids >= 100) & (vids < 500)
+    expect[vids[sel] - 100] = rec[sel, 1:]
+    assert np.array_equal(mirror.cpu().numpy(), expect)
+    L.call("nts_aggregate_records", mirror.data_ptr(), dp, n, F, 100, 500, stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(mirror.cpu().numpy(), expect * 2)
+    L.load().nts_free_pinned(hp)
+
+
+@pytest.mark.parametrize("H", [1, 2, 3, 8])
+def test_edge_softmax_multi_column_with_hub(H):
+    L = lib()
+    rng = np.random.default_rng(H)
+    deg = rng.integers(0, 40, 400)
+    deg[7] = 20000  # block-cooperative path (> kHubDegree)
+    off = np.zeros(401, dtype=np.uint32)
+    np.cumsum(deg, out=off[1:])
+    E = int(off[-1])
+    m = (rng.standard_normal((E, H)) * 4).astype(np.float32)
+    ref = oracle_c.edge_softmax(off, m)
+    d_off, d_m = up_u32(off), up(m)
+    d_a = torch.zeros_like(d_m)
+    d_c = torch.zeros_like(d_m)
+    L.call("nts_edge_softmax_forward", d_a.data_ptr(), d_m.data_ptr(), d_c.data_ptr(), 0, d_off.data_ptr(), 400, H, stream())
+    np.testing.assert_allclose(d_a.cpu().numpy(), ref, rtol=RTOL, atol=1e-7)
+    assert torch.equal(d_a, d_c)
+    g = rng.standard_normal((E, H)).astype(np.float32)
+    d_g = up(g)
+    d_gi = torch.zeros_like(d_g)
+    L.call("nts_edge_softmax_backward", d_gi.data_ptr(), d_g.data_ptr(), d_c.data_ptr(), 0, d_off.data_ptr(), 400, H, stream())
+    np.testing.assert_allclose(d_gi.cpu().numpy(), O.edge_softmax_backward(off, ref, g), rtol=RTOL, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# (3) size-independent properties on a larger graph
+# ------------------------------------------------------------------------------------------------------------
+def test_properties_at_scale():
+    """2M edges, F=602 (the headline width): unweighted aggregation of all-ones counts in-degrees EXACTLY;
+    the weighted op is linear; fwd and bwd are adjoint: <A x, g> == <x, A^T g>."""
+    from neutronstarlite_b200 import ops
+    from neutronstarlite_b200.graph import PartitionedGraph
+    d = dev()
+    V, E, F = 20000, 2_000_000, 602
+    gen = torch.Generator(device=d).manual_seed(0x5EED0001)
+    w = 1.0 / torch.arange(1, V + 1, device=d, dtype=torch.float64)
+    cdf = torch.cumsum(w / w.sum(), 0)
+    perm = torch.randperm(V, generator=gen, device=d)
+    src = perm[torch.searchsorted(cdf, torch.rand(E, generator=gen, device=d, dtype=torch.float64)).clamp_(max=V - 1)]
+    dst = perm[torch.searchsorted(cdf, torch.rand(E, generator=gen, device=d, dtype=torch.float64)).clamp_(max=V - 1)]
+    pg = PartitionedGraph.from_device_edges(src, dst, V)
+    c = pg.graph_chunks[0]
+    ones = torch.ones((V, F), device=d)
+    y = torch.zeros((V, F), device=d)
+    ops.gather_by_dst_from_src(c, y, ones, with_weight=False)
+    indeg = torch.bincount(dst, minlength=V).to(torch.float32)
+    assert torch.equal(y, indeg[:, None].expand(V, F))          # bit-exact integer counts (< 2^24)
+    x1 = torch.rand((V, F), generator=gen, device=d) * 2 - 1
+    x2 = torch.rand((V, F), generator=gen, device=d) * 2 - 1
+    op = ops.ForwardSingleGPUfuseOp(pg)
+    y1, y2, y12 = op.forward(x1), op.forward(x2), op.forward(x1 + 0.5 * x2)
+    torch.testing.assert_close(y12, y1 + 0.5 * y2, rtol=RTOL, atol=1e-4)
+    g = torch.rand((V, F), generator=gen, device=d) * 2 - 1
+    lhs = (y1.double() * g.double()).sum()
+    rhs = (x1.double() * op.backward(g).double()).sum()
+    assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs))
+    # device-built chunk == host-built chunk (bit-exact arrays) on a slice small enough for the host path
+    from neutronstarlite_b200.graph import HostGraph
+    sub = 200_000
+    e_np = torch.stack([src[:sub], dst[:sub]], 1).cpu().numpy().astype(np.uint32)
+    hpg = PartitionedGraph(HostGraph(e_np, V), 1, 0).generate_all()
+    dpg = PartitionedGraph.from_device_edges(src[:sub], dst[:sub], V)
+    hc, dc = hpg.graph_chunks[0], dpg.graph_chunks[0]
+    for name in ("column_offset", "row_indices", "row_offset", "column_indices"):
+        assert np.array_equal(getattr(hc, name).view(np.int32), getattr(dc, name + "_gpu").cpu().numpy()), name
+    for name in ("edge_weight_forward", "edge_weight_backward"):
+        assert np.array_equal(getattr(hc, name).view(np.uint32),
+                              getattr(dc, name + "_gpu").cpu().numpy().view(np.uint32)), name
