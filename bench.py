@@ -1,0 +1,397 @@
+#!/usr/bin/env python3
+"""bench.py - the headline benchmark of BASELINE.json: GCN epochs/s and aggregated-edges/s on the Reddit-shaped
+synthetic graph (232 965 V, 114.6 M power-law edges + self loops, LAYERS 602-128-41, fp32), N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit|products|tiny]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1: one rank per GPU, NCCL)
+
+One step = one GCN training epoch through the reference-shaped API (toolkits.GCNImpl <-> toolkits/GCN.hpp):
+3 aggregation calls (fwd 602, fwd 128, bwd 128) + the dense GEMMs, loss, tape backward, Adam (+ NCCL gradient
+all-reduce for N > 1).  N > 1 partitions the SAME graph with the reference's partitioner (strong scaling).
+
+Prints ONE JSON line (rank 0).  `value` = aggregated edges per second over the whole job (3*E / epoch time) with
+inputs resident in HBM; `e2e` = the same with the feature matrix coming from pinned host memory every step and the
+loss read back; `roofline` = the layer-0 forward aggregation kernel (F=602) timed live with CUDA events;
+`cpu_baseline` / `--impl reference` = the UNMODIFIED reference CPU GCN (toolkits/GCN_CPU.hpp via oracle/_ref, built
+from /root/reference by oracle/Makefile) on a bounded edge sample of the same workload on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit")
+    ap.add_argument("--transport", default=os.environ.get("NTS_TRANSPORT", "nccl"), choices=["nccl", "p2p"])
+    ap.add_argument("--variant", type=int, default=0, help="aggregation kernel variant (0 auto, 1 shuffle, 2 bulk)")
+    ap.add_argument("--edges-per-warp", type=int, default=0)
+    ap.add_argument("--drop-rate", type=float, default=0.5)
+    ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline runs on E/div edges")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index=0):
+        self.proc = None
+        self.lines = []
+        self.idx = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref/nts_ref_main = the reference's stock main.cpp + GCN_CPU.hpp, unmodified)
+# ---------------------------------------------------------------------------------------------------------------
+def reference_cpu_epochs(V, layers, edges_u32, steps, warmup, threads=None):
+    """Run ALGORITHM:GCNCPU of the unmodified reference on `edges_u32` ([E,2] numpy) for warmup+steps epochs and
+    time epochs from its own per-epoch log lines.  Returns dict(value edges/s, s_per_epoch, cores, kind)."""
+    import numpy as np
+    binary = os.path.join(ROOT, "oracle", "_ref", "nts_ref_main")
+    cores = threads or os.cpu_count()
+    E = int(edges_u32.shape[0])
+    if not os.path.exists(binary):
+        return _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores)
+    work = tempfile.mkdtemp(prefix="nts_bench_ref_")
+    try:
+        efile = os.path.join(work, "g.edge")
+        edges_u32.astype(np.uint32).tofile(efile)
+        cfg = os.path.join(work, "g.cfg")
+        with open(cfg, "w") as f:
+            f.write("ALGORITHM:GCNCPU\nVERTICES:%d\nLAYERS:%s\nEPOCHS:%d\nEDGE_FILE:%s\nFEATURE_FILE:random\n"
+                    "LABEL_FILE:random\nMASK_FILE:random\nPROC_OVERLAP:0\nPROC_LOCAL:0\nPROC_CUDA:0\nPROC_REP:0\n"
+                    "LOCK_FREE:1\nLEARN_RATE:0.01\nWEIGHT_DECAY:0.0001\nDECAY_RATE:0.97\nDECAY_EPOCH:100\n"
+                    "DROP_RATE:0.0\n" % (V, "-".join(str(x) for x in layers), warmup + steps, efile))
+        env = dict(os.environ)
+        env["NTS_THREADS"] = str(cores)
+        env["OMP_NUM_THREADS"] = str(cores)
+        proc = subprocess.Popen([binary, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+        stamps = []
+        for line in proc.stdout:
+            if "Running.Epoch[" in line:
+                stamps.append(time.perf_counter())
+        proc.wait()
+        if proc.returncode != 0 or len(stamps) < warmup + steps:
+            return _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores)
+        # epoch k ends at stamps[k]; timed region = epochs warmup .. warmup+steps-1
+        t = stamps[warmup + steps - 1] - stamps[warmup - 1] if warmup >= 1 else None
+        if t is None:
+            t = (stamps[-1] - stamps[0]) * steps / max(1, len(stamps) - 1)
+        s_per_epoch = t / steps
+        return {"value": 3.0 * E / s_per_epoch, "unit": "edges/s", "s_per_epoch": s_per_epoch, "cores": cores,
+                "kind": "reference"}
+    finally:
+        import shutil
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores):
+    """Fallback when the reference binary is absent: the plain-C port of the aggregation loops (oracle/nts_oracle.c),
+    aggregation calls only (fwd F0, fwd F1, bwd F1)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c
+    import nts_oracle as O
+    po = np.array([0, V], dtype=np.uint32)
+    c = O.build_chunks(edges_u32, V, po, 0)[0]
+    rng = np.random.default_rng(0)
+    xs = [rng.uniform(-1, 1, (V, f)).astype(np.float32) for f in layers[:-1]]
+    ts = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for li, x in enumerate(xs):
+            oracle_c.segment_gather_sum(c.column_offset, c.row_indices, c.edge_weight_forward, x)
+            if li > 0:
+                oracle_c.segment_gather_sum(c.row_offset, c.column_indices, c.edge_weight_backward, x)
+        ts.append(time.perf_counter() - t0)
+    s = sum(ts[warmup:]) / steps
+    return {"value": 3.0 * edges_u32.shape[0] / s, "unit": "edges/s", "s_per_epoch": s, "cores": cores, "kind": "port"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from neutronstarlite_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    V, E_rand, layers = synth.WORKLOADS[args.workload]
+    E_total = E_rand + V
+
+    # ------------------------------------------------------------------ reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        div = max(1, args.cpu_sample_div)
+        edges = _sample_edges_cpu(V, E_rand, div)
+        res = reference_cpu_epochs(V, layers, edges, args.steps, args.warmup)
+        sample = "first 1/%d of the workload's random edges + all self loops (%d edges), all V, full widths" % (
+            div, edges.shape[0])
+        line = {
+            "impl": "reference", "metric": "gcn_aggregated_edges_per_sec", "value": res["value"], "unit": "edges/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["s_per_epoch"] * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "epochs_per_sec": 1.0 / res["s_per_epoch"],
+            "config": {"workload": _workload_name(args.workload, V, E_total, layers), "sample": sample,
+                       "parallelism": "cpu x%d threads" % res["cores"]},
+            "cpu_baseline": {"value": res["value"], "unit": "edges/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": sample},
+            "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - libnts_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    from neutronstarlite_b200 import _lib, ops
+    from neutronstarlite_b200.exchange import GpuExchange
+    from neutronstarlite_b200.graph import PartitionedGraph, partition_offsets_from_out_degree
+    from neutronstarlite_b200.toolkits import GCNImpl
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.call("nts_aggregate_set_variant", args.variant, args.edges_per_warp)
+
+    # graph: every rank generates the same edge list (same seed), keeps only what it owns
+    src, dst = synth.zipf_edges(V, E_rand, dev)
+    out_raw = torch.bincount(src, minlength=V)
+    out_deg = out_raw.clamp(min=1)
+    in_deg = torch.bincount(dst, minlength=V).clamp_(min=1)
+    po = partition_offsets_from_out_degree(out_raw.cpu().numpy(), E_total, world)
+    pg = PartitionedGraph.from_device_edges(src, dst, V, world, rank, po, out_deg, in_deg)
+    del src, dst
+    torch.cuda.empty_cache()
+    v0, v1 = int(po[rank]), int(po[rank + 1])
+    feats, labels, mask = synth.features_labels_mask(V, layers[0], layers[-1], dev, rows=(v0, v1))
+    op_kwargs = {}
+    if world > 1:
+        op_kwargs["exchange"] = GpuExchange(pg, transport=args.transport)
+    model = GCNImpl(pg, layers, feats, labels, mask, drop_rate=args.drop_rate, op_kwargs=op_kwargs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(3, args.warmup)):
+        model.run_epoch()
+    barrier()
+
+    # ---- timed region A: inputs resident in HBM
+    timer = ops.KernelTimer()
+    ops.set_kernel_timer(timer)
+    launches0 = lib.nts_kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.nvtx.range_push("nts_timed")
+    ev0.record()
+    for _ in range(args.steps):
+        model.run_epoch()
+    ev1.record()
+    barrier()
+    torch.cuda.nvtx.range_pop()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.nts_kernel_launch_count() - launches0
+    ops.set_kernel_timer(None)
+    ksum = timer.summary()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = 3.0 * E_total / (ms_step * 1e-3)
+
+    # ---- timed region B: end to end through the public API with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        host_feats = torch.empty(feats.shape, dtype=torch.float32).pin_memory()
+        host_feats.copy_(feats)
+        host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+        dev_in = torch.empty_like(feats)
+
+        def e2e_step():
+            dev_in.copy_(host_feats, non_blocking=True)
+            model.X[0] = dev_in.requires_grad_(True)
+            loss, _ = model.run_epoch()
+            host_loss.copy_(loss.detach(), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item()) / args.steps
+        hb = torch.tensor([feats.numel() * 4], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(hb)
+        e2e = {"value": 3.0 * E_total / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(hb.item()), "d2h_bytes_per_step": 4 * world}
+
+    # ---- roofline of the dominant kernel: layer-0 forward aggregation (widest F), this rank's launches
+    F0 = layers[0]
+    k = ksum.get(("fwd", F0))
+    roof = None
+    if k and k["ms"] > 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        # algorithmic bytes: E*(4 idx + 4 w + 4F row) + V_out*4F + (V_out+1)*4, summed over launches
+        b_alg = k["edges"] * (8 + 4 * F0) + k["rows"] * 4 * F0 + (k["rows"] + k["calls"]) * 4
+        achieved = b_alg / (k["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "segment_gather_sum_kernel (fwd, F=%d)" % F0, "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
+                "traffic": _ncu_traffic(), "launches": k["calls"], "avg_ms_per_launch": k["ms"] / k["calls"],
+                "algorithmic_bytes_per_launch": b_alg / k["calls"]}
+    kernels = {"%s_F%d" % (tag, F): {"calls": d["calls"], "avg_ms": d["ms"] / d["calls"],
+                                      "gedges_per_s": d["edges"] / (d["ms"] * 1e-3) / 1e9}
+               for (tag, F), d in ksum.items()}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            div = max(1, args.cpu_sample_div)
+            edges = _sample_edges_cpu(V, E_rand, div)
+            r = reference_cpu_epochs(V, layers, edges, 2, 1)
+            cpu = {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
+                   "s_per_epoch": r["s_per_epoch"],
+                   "sample": "first 1/%d of the workload's random edges + all self loops (%d edges), all V, full "
+                             "widths; unmodified reference ALGORITHM:GCNCPU, 1 warm-up + 2 timed epochs" % (
+                                 div, edges.shape[0])}
+        line = {
+            "metric": "gcn_aggregated_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "epochs_per_sec": 1e3 / ms_step,
+            "config": {"workload": _workload_name(args.workload, V, E_total, layers),
+                       "parallelism": "graph-partition x%d (reference partitioner), %s exchange" % (world, args.transport)
+                       if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (features %.0f MB, graph arrays %.0f MB per rank)" % (
+                           feats.numel() * 4 / 1e6, pg.owned_edges * 16 / 1e6),
+                       "drop_rate": args.drop_rate, "kernel_variant": args.variant or 1},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "kernels": kernels, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _workload_name(name, V, E, layers):
+    return "%s-shaped synthetic power-law graph: %d V, %d E (incl. self loops), 2-layer GCN %s fp32" % (
+        name, V, E, "-".join(str(x) for x in layers))
+
+
+def _sample_edges_cpu(V, E_rand, div):
+    """The first 1/div of the workload's random edges + all self loops as a [E,2] uint32 numpy array, generated with
+    the same Zipf law on the CPU (the reference arm must not need a GPU)."""
+    import numpy as np
+    import torch
+    from neutronstarlite_b200 import synth
+    n = E_rand // div
+    src, dst = synth.zipf_edges(V, n, torch.device("cpu"))
+    return torch.stack([src, dst], 1).numpy().astype(np.uint32)
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get("dram_bytes_per_launch_fwd_F602")
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,118 @@
+"""`NtsContext`: the reference's hand-rolled autograd tape (core/ntsContext.hpp:96-409), host side only.
+
+Graph operators run hand-written kernels outside torch's autograd; NN segments between them are ordinary torch
+autograd graphs.  The tape records, in execution order, GRAPHOP / BIGRAPHOP entries (operator object kept for its
+`backward`) and NNOP entries (only the boundary tensors; consecutive NN ops are chained into one entry,
+ntsContext.hpp:228-251).  `self_backward` pops the tape exactly like the reference (:276-359), including its
+quirk that the loop stops when a single GRAPHOP is left: the FIRST graph operator of a model that starts with one
+(GCN.hpp) is never back-propagated (`while (count > 1 || (count == 1 && NNOP == op.top()))`, :283)."""
+from __future__ import annotations
+
+import torch
+
+GRAPHOP, BIGRAPHOP, NNOP = "GRAPHOP", "BIGRAPHOP", "NNOP"
+
+
+class _Entry:
+    __slots__ = ("kind", "op", "input", "output", "o_id", "i_id1", "i_id2", "grad")
+
+    def __init__(self, kind, op, inp, out, i_id2=None):
+        self.kind, self.op, self.input, self.output = kind, op, inp, out
+        self.o_id = out.data_ptr()
+        self.i_id1 = inp.data_ptr()
+        self.i_id2 = i_id2
+        self.grad = None
+
+
+class NtsContext:
+    def __init__(self):
+        self.tape = []
+        self.training = True
+
+    @property
+    def count(self):
+        return len(self.tape)
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    # ---- forward recording -------------------------------------------------------------------------------
+    def runGraphOp(self, op_class, partitioned_graph, active, f_input, f_input2=None, **op_kwargs):
+        """ntsContext.hpp:108-149 (one- and two-input graph operators)."""
+        op = op_class(partitioned_graph, active, **op_kwargs)
+        if f_input2 is None:
+            out = op.forward(f_input)
+            out.requires_grad_(True)  # NewKeyTensor: outputs are leaves that collect gradients
+            if self.training:
+                self.tape.append(_Entry(GRAPHOP, op, f_input, out))
+        else:
+            out = op.forward(f_input, f_input2)
+            out.requires_grad_(True)
+            self.tape.append(_Entry(BIGRAPHOP, op, f_input, out, f_input2.data_ptr()))
+        return out
+
+    def runVertexForward(self, vertexforward, nbr_input, vtx_input=None):
+        """ntsContext.hpp:198-216."""
+        out = vertexforward(nbr_input) if vtx_input is None else vertexforward(nbr_input, vtx_input)
+        if self.training:
+            self.appendNNOp(nbr_input, out)
+        return out
+
+    def runEdgeForward(self, edgeforward, edge_input):
+        """ntsContext.hpp:218-226."""
+        out = edgeforward(edge_input)
+        if self.training:
+            self.appendNNOp(edge_input, out)
+        return out
+
+    def appendNNOp(self, input_t, output_t):
+        """ntsContext.hpp:228-251: chain onto the previous NNOP when this op consumes its output."""
+        assert self.training
+        if self.tape and self.tape[-1].kind == NNOP and input_t.data_ptr() == self.tape[-1].o_id:
+            self.tape[-1].output = output_t
+            self.tape[-1].o_id = output_t.data_ptr()
+        else:
+            self.tape.append(_Entry(NNOP, None, input_t, output_t))
+
+    # ---- backward --------------------------------------------------------------------------------------------
+    def _producer_of(self, data_ptr, upto):
+        for k in range(upto, -1, -1):
+            if self.tape[k].o_id == data_ptr:
+                return k
+        return -1
+
+    def self_backward(self, retain_graph=True):
+        """ntsContext.hpp:276-359."""
+        assert self.training and self.tape
+        top = self.tape[-1]
+        top.output.backward(torch.ones_like(top.output), retain_graph=retain_graph)
+        if len(self.tape) >= 2:
+            self.tape[-2].grad = top.input.grad
+        self.tape.pop()
+        while len(self.tape) > 1 or (len(self.tape) == 1 and self.tape[-1].kind == NNOP):
+            e = self.tape[-1]
+            idx = len(self.tape) - 1
+            if e.grad is None or e.grad.dim() < 2:
+                e.grad = e.output.grad
+            if e.kind in (GRAPHOP, BIGRAPHOP):
+                g_in = e.op.backward(e.grad)
+                k = self._producer_of(e.i_id1, idx)
+                if k >= 0:
+                    self.tape[k].grad = g_in
+                if e.kind == BIGRAPHOP:
+                    k2 = self._producer_of(e.i_id2, idx)
+                    if k2 >= 0:
+                        self.tape[k2].grad = e.op.get_additional_grad()
+            else:  # NNOP: torch autograd carries the gradient through the NN segment
+                if e.grad is not None and e.grad.dim() > 1:
+                    assert e.grad.shape == e.output.shape
+                    e.output.backward(e.grad, retain_graph=retain_graph)
+            self.tape.pop()
+        self.reset()
+
+    def reset(self):
+        assert len(self.tape) <= 1
+        self.tape = []

@@ -1,0 +1,430 @@
+"""Device-resident partition-boundary exchange: the B200 replacement for the reference's host-staged MPI ring
+(`Graph::sync_compute_decoupled` / `compute_sync_decoupled`, core/graph.hpp:3455-3719, and `NtsGraphCommunicator`,
+comm/network.cpp:159-844).
+
+What moves, and when (rank p of P, partition i -> chunk i = edges src in part i -> dst in part p):
+
+  forward   Y_p = sum_i A_{p<-i} X_i.  Rank p needs, from every other rank i, only the rows of X_i that are sources
+            of chunk i (`source_active`, core/PartitionedGraph.hpp:397) - M_{p<-i} dense rows, no (vid,row) records.
+            They land in a staging buffer indexed by a compact slot; chunk i's CSC indices are remapped to slots
+            once at setup, so the aggregation kernel consumes the received rows with no unpack pass.  The local
+            chunk (i == p) aggregates while the rows are in flight; remote chunks follow in the reference's ring
+            order (p+1, p+2, ... mod P; core/graph.hpp:3678-3683).
+  backward  dX_p = sum_j A_{j<-p}^T dY_j.  Rank p computes, per chunk i, the partial gradients of the ACTIVE sources
+            only (CSR compacted to active rows -> [M_{p<-i}, F], written straight into the send staging), ships them
+            to i, and adds what it receives for its own rows with one unique-row scatter-add per peer
+            (replaces aggregate_data_buffer_debug's per-element atomics, cuda/ntsCUDATransferKernel.cuh:49-68).
+
+Transports:
+  "nccl"  one all-to-all(v) of the packed rows (torch.distributed / NCCL over NVLink), on a side stream.
+  "p2p"   no packing and no NCCL on the data path: every rank exports its [V_p, F] buffer through CUDA IPC and the
+          RECEIVER pulls the rows it needs straight out of the peer's HBM over NVLink with `nts_gather_rows` on
+          mapped peer pointers; completion is stream-ordered locally, cross-rank ordering uses system-scope flags
+          (`nts_signal_set` / `nts_signal_wait_geq`).  Chunk i+1 is pulled while chunk i aggregates.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import ops
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class ExchangePlan:
+    """Setup-time index structures (per PartitionedGraph).  Backend-agnostic: built with torch ops on whatever
+    device the chunk arrays live on and torch.distributed collectives (works with gloo on CPU tensors)."""
+
+    def __init__(self, pg, group=None):
+        self.pg = pg
+        self.P = pg.partitions
+        self.p = pg.partition_id
+        self.group = group
+        P, p = self.P, self.p
+        chunks = pg.graph_chunks
+        dev = chunks[0].column_offset_gpu.device if chunks[0].column_offset_gpu is not None else torch.device("cpu")
+        self.device = dev
+        self.need = [None] * P            # need[i]: int32 local ids (within partition i) of the rows of X_i I read
+        self.csc_slots = [None] * P       # chunk i's row_indices remapped to staging slots (int32 [E_i])
+        self.csr_offsets_compact = [None] * P  # chunk i's row_offset restricted to active rows (int32 [M_i+1])
+        for i in range(P):
+            c = chunks[i]
+            ro = self._arr(c, "row_offset").to(torch.int64)
+            deg = ro[1:] - ro[:-1]
+            active = torch.nonzero(deg > 0).view(-1)
+            self.need[i] = active.to(torch.int32)
+            if i != p:
+                slot_of = torch.zeros(c.batch_size_backward, dtype=torch.int32, device=dev)
+                slot_of[active] = torch.arange(active.numel(), dtype=torch.int32, device=dev)
+                ri = self._arr(c, "row_indices").to(torch.int64) - c.src_range[0]
+                self.csc_slots[i] = slot_of[ri] if ri.numel() else torch.zeros(0, dtype=torch.int32, device=dev)
+                self.csr_offsets_compact[i] = torch.cat([ro[active], ro[-1:]]).to(torch.int32)
+        self.need_count = [int(n.numel()) for n in self.need]
+        # tell every peer which of its rows I need (forward) == which rows it will get gradients for (backward)
+        self.send_rows = [None] * P
+        counts_in = torch.tensor([self.need_count[i] if i != p else 0 for i in range(P)], dtype=torch.int64)
+        counts_out = torch.zeros(P, dtype=torch.int64)
+        if P > 1:
+            cdev = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            ci, co = counts_in.to(cdev), counts_out.to(cdev)
+            dist.all_to_all_single(co, ci, group=group)
+            counts_out = co.cpu()
+            send = torch.cat([self.need[i] if i != p else self.need[i][:0] for i in range(P)]).to(cdev)
+            recv = torch.zeros(int(counts_out.sum()), dtype=torch.int32, device=cdev)
+            dist.all_to_all_single(recv, send, output_split_sizes=counts_out.tolist(),
+                                   input_split_sizes=counts_in.tolist(), group=group)
+            pos = 0
+            for j in range(P):
+                n = int(counts_out[j])
+                self.send_rows[j] = recv[pos:pos + n].to(dev)
+                pos += n
+        self.send_count = [0 if r is None else int(r.numel()) for r in self.send_rows]
+        if P == 1:
+            self.send_rows = [None]
+        self.recv_total = sum(self.need_count[i] for i in range(P) if i != p)
+        self.send_total = sum(self.send_count[j] for j in range(P) if j != p)
+
+    @staticmethod
+    def _arr(c, name):
+        g = getattr(c, name + "_gpu")
+        if g is not None:
+            return g
+        return torch.from_numpy(getattr(c, name).view(np.int32))
+
+    def ring(self):
+        """Remote chunks in the reference's processing order: (p+1), (p+2), ... mod P."""
+        return [(self.p + s) % self.P for s in range(1, self.P)]
+
+
+class GpuExchange:
+    """Forward / backward drivers of the distributed fused aggregation on one GPU per rank."""
+
+    def __init__(self, pg, transport="nccl", group=None):
+        if not torch.cuda.is_available():
+            raise _lib.NtsError("GpuExchange needs a CUDA device (libnts_b200 has no CPU fallback)")
+        self.pg = pg
+        self.P, self.p = pg.partitions, pg.partition_id
+        self.group = group
+        self.plan = ExchangePlan(pg, group)
+        self.transport = transport
+        self.device = self.plan.device
+        self.comm_stream = torch.cuda.Stream(device=self.device)
+        self._staging = {}
+        self._p2p = None
+        if transport == "p2p" and self.P > 1:
+            self._p2p = _PeerWindows(self)
+        elif transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
+
+    # ---- buffers ---------------------------------------------------------------------------------------------
+    def _buf(self, key, rows, F):
+        t = self._staging.get((key, F))
+        if t is None or t.shape[0] < rows:
+            t = torch.empty((max(rows, 1), F), dtype=torch.float32, device=self.device)
+            self._staging[(key, F)] = t
+        return t[:rows]
+
+    # ---- forward -----------------------------------------------------------------------------------------------
+    def forward(self, x):
+        pg, plan, P, p = self.pg, self.plan, self.P, self.p
+        F = x.shape[1]
+        y = torch.zeros((pg.owned_vertices, F), dtype=torch.float32, device=x.device)
+        cur = torch.cuda.current_stream()
+        if P == 1:
+            return ops.gather_by_dst_from_src(pg.graph_chunks[0], y, x)
+        if self._p2p is not None:
+            return self._forward_p2p(x, y)
+        # pack the rows every peer needs, exchange on the side stream
+        send = self._buf("fsend", plan.send_total, F)
+        recv = self._buf("frecv", plan.recv_total, F)
+        pos = 0
+        for j in range(P):
+            n = plan.send_count[j]
+            if j != p and n:
+                _lib.call("nts_gather_rows", _ptr(send[pos:pos + n]), _ptr(x), _ptr(plan.send_rows[j]), n, F,
+                          cur.cuda_stream)
+                pos += n
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            in_split = [plan.send_count[j] if j != p else 0 for j in range(P)]
+            out_split = [plan.need_count[i] if i != p else 0 for i in range(P)]
+            dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split,
+                                   group=self.group)
+        # local chunk overlaps with the transfer
+        ops.gather_by_dst_from_src(pg.graph_chunks[p], y, x)
+        cur.wait_stream(self.comm_stream)
+        recv.record_stream(cur)
+        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
+        for i in plan.ring():
+            c = pg.graph_chunks[i]
+            if c.edge_size == 0:
+                continue
+            seg = recv[int(offs[i]):int(offs[i + 1])]
+            self._aggregate_slots(c, plan.csc_slots[i], y, seg)
+        return y
+
+    def _aggregate_slots(self, c, slots, y, staged):
+        """Chunk aggregation from a compact staging buffer: indices are slots, base 0."""
+        ev = ops._timer.bracket("fwd", staged.shape[1], c.edge_size, c.batch_size_forward) if ops._timer else None
+        if ev:
+            ev[0].record()
+        _lib.call("nts_segment_gather_sum", _ptr(staged), _ptr(y), _ptr(c.edge_weight_forward_gpu), _ptr(slots),
+                  _ptr(c.column_offset_gpu), 0, c.batch_size_forward, c.edge_size, staged.shape[1],
+                  torch.cuda.current_stream().cuda_stream)
+        if ev:
+            ev[1].record()
+
+    # ---- backward ----------------------------------------------------------------------------------------------
+    def backward(self, g):
+        pg, plan, P, p = self.pg, self.plan, self.P, self.p
+        F = g.shape[1]
+        dx = torch.zeros((pg.owned_vertices, F), dtype=torch.float32, device=g.device)
+        cur = torch.cuda.current_stream()
+        if P == 1:
+            return ops.gather_by_src_from_dst(pg.graph_chunks[0], dx, g)
+        if self._p2p is not None:
+            return self._backward_p2p(g, dx)
+        # partial gradients of the active sources of every remote chunk, written straight into the send staging
+        send = self._buf("bsend", plan.recv_total, F)
+        recv = self._buf("brecv", plan.send_total, F)
+        send.zero_()
+        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
+        for i in plan.ring():
+            c = pg.graph_chunks[i]
+            if c.edge_size == 0:
+                continue
+            seg = send[int(offs[i]):int(offs[i + 1])]
+            self._partial_compact(c, plan.csr_offsets_compact[i], seg, g)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            in_split = [plan.need_count[i] if i != p else 0 for i in range(P)]
+            out_split = [plan.send_count[j] if j != p else 0 for j in range(P)]
+            dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split,
+                                   group=self.group)
+        ops.gather_by_src_from_dst(pg.graph_chunks[p], dx, g)   # local chunk overlaps with the transfer
+        cur.wait_stream(self.comm_stream)
+        recv.record_stream(cur)
+        pos = 0
+        for j in range(P):
+            n = plan.send_count[j]
+            if j != p and n:
+                _lib.call("nts_scatter_add_rows", _ptr(dx), _ptr(recv[pos:pos + n]), _ptr(plan.send_rows[j]), n, F,
+                          cur.cuda_stream)
+                pos += n
+        return dx
+
+    def _partial_compact(self, c, offsets_compact, out_rows, g):
+        ev = ops._timer.bracket("bwd", g.shape[1], c.edge_size, out_rows.shape[0]) if ops._timer else None
+        if ev:
+            ev[0].record()
+        _lib.call("nts_segment_gather_sum", _ptr(g), _ptr(out_rows), _ptr(c.edge_weight_backward_gpu),
+                  _ptr(c.column_indices_gpu), _ptr(offsets_compact), c.dst_range[0], out_rows.shape[0],
+                  c.edge_size, g.shape[1], torch.cuda.current_stream().cuda_stream)
+        if ev:
+            ev[1].record()
+
+    # ---- peer-memory transport ------------------------------------------------------------------------------------
+    def _forward_p2p(self, x, y):
+        pg, plan, P, p = self.pg, self.plan, self.P, self.p
+        F = x.shape[1]
+        w = self._p2p
+        cur = torch.cuda.current_stream()
+        # publish my rows: copy into the exported window (the op input is borrowed torch storage, not IPC memory)
+        w.reserve(pg.owned_vertices, plan.recv_total, F)
+        epoch = w.begin(cur)
+        _lib.call("nts_memcpy_d2d", w.window, x.data_ptr(), x.numel() * 4, cur.cuda_stream)
+        w.commit(epoch, cur)
+        ops.gather_by_dst_from_src(pg.graph_chunks[p], y, x)     # local chunk while peers publish
+        recv = self._buf("frecv", plan.recv_total, F)
+        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
+        ring = plan.ring()
+        # pull chunk i+1 on the side stream while chunk i aggregates on the main stream
+        pulled = []
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            for i in ring:
+                n = plan.need_count[i]
+                seg = recv[int(offs[i]):int(offs[i + 1])]
+                if n:
+                    w.wait_published(i, epoch, self.comm_stream)
+                    _lib.call("nts_gather_rows", _ptr(seg), w.peer_ptr(i), _ptr(plan.need[i]), n, F,
+                              self.comm_stream.cuda_stream)
+                ev = torch.cuda.Event()
+                ev.record(self.comm_stream)
+                pulled.append(ev)
+            w.signal_consumed(epoch, self.comm_stream)
+        recv.record_stream(self.comm_stream)
+        for k, i in enumerate(ring):
+            c = pg.graph_chunks[i]
+            cur.wait_event(pulled[k])
+            if c.edge_size:
+                self._aggregate_slots(c, plan.csc_slots[i], y, recv[int(offs[i]):int(offs[i + 1])])
+        return y
+
+    def _backward_p2p(self, g, dx):
+        pg, plan, P, p = self.pg, self.plan, self.P, self.p
+        F = g.shape[1]
+        w = self._p2p
+        cur = torch.cuda.current_stream()
+        # my partials for every peer go into MY exported window; peers pull their slice and add it
+        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
+        w.reserve(pg.owned_vertices, plan.recv_total, F)
+        epoch = w.begin(cur)                       # peers are done with what I published last time
+        win = w.window_rows(plan.recv_total, F)
+        win.zero_()
+        for i in plan.ring():
+            c = pg.graph_chunks[i]
+            if c.edge_size:
+                self._partial_compact(c, plan.csr_offsets_compact[i], win[int(offs[i]):int(offs[i + 1])], g)
+        w.commit(epoch, cur)
+        ops.gather_by_src_from_dst(pg.graph_chunks[p], dx, g)
+        # pull from every peer j the slice it computed for me: rows offs_j[p] .. of ITS window
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            for j in plan.ring():
+                n = plan.send_count[j]
+                if n:
+                    w.wait_published(j, epoch, self.comm_stream)
+                    src = w.peer_ptr(j) + int(w.peer_bwd_offset[j]) * F * 4
+                    tmp = self._buf("brecv%d" % j, n, F)
+                    _lib.call("nts_memcpy_d2d", _ptr(tmp), src, n * F * 4, self.comm_stream.cuda_stream)
+                    _lib.call("nts_scatter_add_rows", _ptr(dx), _ptr(tmp), _ptr(plan.send_rows[j]), n, F,
+                              self.comm_stream.cuda_stream)
+            w.signal_consumed(epoch, self.comm_stream)
+        cur.wait_stream(self.comm_stream)
+        return dx
+
+
+class _PeerWindows:
+    """CUDA-IPC windows: one exported device buffer per rank (rows published per call) plus two uint32 flag arrays
+    (published[rank], consumed[rank][peer]) for cross-GPU ordering.  Control plane: torch.distributed
+    (all_gather_object of the 64-byte IPC handles)."""
+
+    def __init__(self, ex):
+        self.ex = ex
+        P, p = ex.P, ex.p
+        self.P, self.p = P, p
+        L = _lib.load()
+        pg, plan = ex.pg, ex.plan
+        self.capacity_floats = 0
+        self.window = 0
+        self.flags = L.nts_malloc_device(4 * (1 + P))
+        if not self.flags:
+            raise _lib.NtsError("flag allocation failed: " + L.nts_last_error().decode())
+        _lib.call("nts_zero", self.flags, 4 * (1 + P), 0)
+        _lib.call("nts_device_synchronize")
+        self.epoch = 0
+        self._peers = None
+        # backward: where my slice starts inside peer j's window = offset of chunk p in j's remote-chunk order
+        mine = torch.tensor([plan.need_count[i] if i != p else 0 for i in range(P)], dtype=torch.int64)
+        allc = [None] * P
+        dist.all_gather_object(allc, mine.tolist(), group=ex.group)
+        self.peer_bwd_offset = [int(sum(allc[j][:p])) for j in range(P)]
+        self._handle_flags = self._export(self.flags)
+        self._reserved = set()
+
+    def _export(self, ptr):
+        import ctypes
+        buf = ctypes.create_string_buffer(_lib.C.sizeof(_lib.C.c_char) * 64)
+        _lib.call("nts_ipc_get_handle", ptr, buf)
+        return bytes(buf.raw)
+
+    def _ensure(self, floats):
+        """(Re)allocate the exported window so it holds `floats` float32 and re-open every peer's window."""
+        L = _lib.load()
+        P, p = self.P, self.p
+        need = torch.tensor([floats], dtype=torch.int64, device=self.ex.device)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.ex.group)
+        floats = int(need.item())
+        if floats <= self.capacity_floats:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.ex.group)
+        if self._peers:
+            for j, (w, f) in enumerate(self._peers):
+                if j != p:
+                    L.nts_ipc_close_handle(w)
+                    L.nts_ipc_close_handle(f)
+        if self.window:
+            L.nts_free_device(self.window)
+        self.window = L.nts_malloc_device(floats * 4)
+        if not self.window:
+            raise _lib.NtsError("window allocation failed: " + L.nts_last_error().decode())
+        self.capacity_floats = floats
+        handles = [None] * P
+        dist.all_gather_object(handles, (self._export(self.window), self._handle_flags), group=self.ex.group)
+        self._peers = []
+        for j in range(P):
+            if j == p:
+                self._peers.append((self.window, self.flags))
+            else:
+                w = L.nts_ipc_open_handle(handles[j][0])
+                f = L.nts_ipc_open_handle(handles[j][1])
+                if not w or not f:
+                    raise _lib.NtsError("cudaIpcOpenMemHandle failed: " + L.nts_last_error().decode())
+                self._peers.append((w, f))
+        dist.barrier(group=self.ex.group)
+
+    def peer_ptr(self, j):
+        return self._peers[j][0]
+
+    def reserve(self, owned_rows, recv_rows, F):
+        """Make sure the window holds max(owned_rows, recv_rows) x F floats on every rank (collective, first use
+        of a feature width only)."""
+        if F in self._reserved:
+            return
+        self._ensure(max(owned_rows, recv_rows, 1) * F)
+        self._reserved.add(F)
+
+    def window_rows(self, rows, F):
+        arr = _WindowArray(self.window, max(rows, 1) * F)
+        return torch.as_tensor(arr, device=self.ex.device).view(torch.float32)[: rows * F].view(rows, F)
+
+    def begin(self, stream):
+        """Open a new publication epoch: wait (on `stream`) until every peer has consumed my previous one."""
+        self.epoch += 1
+        e = self.epoch
+        if e > 1:
+            for j in range(self.P):
+                if j != self.p:
+                    _lib.call("nts_signal_wait_geq", self.flags + 4 * (1 + j), e - 1, stream.cuda_stream)
+        return e
+
+    def commit(self, epoch, stream):
+        """Everything written to the window so far on `stream` becomes visible to the peers."""
+        _lib.call("nts_signal_set", self.flags, epoch, stream.cuda_stream)
+
+    def wait_published(self, j, epoch, stream):
+        _lib.call("nts_signal_wait_geq", self._peers[j][1], epoch, stream.cuda_stream)
+
+    def signal_consumed(self, epoch, stream):
+        """Tell every peer I am done reading its window for this epoch: set consumed[me] in THEIR flag array."""
+        for j in range(self.P):
+            if j != self.p:
+                _lib.call("nts_signal_set", self._peers[j][1] + 4 * (1 + self.p), epoch, stream.cuda_stream)
+
+
+class _WindowArray:
+    """__cuda_array_interface__ view of a raw device allocation (bytes as uint8 -> viewed as float32)."""
+
+    def __init__(self, ptr, floats):
+        self.__cuda_array_interface__ = {
+            "shape": (floats * 4,), "typestr": "|u1", "data": (int(ptr), False), "version": 2,
+        }
+
+
+_default = {}
+
+
+def default_exchange(pg):
+    """One exchange object per PartitionedGraph (created lazily by ForwardGPUfuseOp)."""
+    ex = _default.get(id(pg))
+    if ex is None:
+        ex = GpuExchange(pg, transport="nccl")
+        _default[id(pg)] = ex
+    return ex

@@ -21,6 +21,34 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+PAGESIZE = 1 << 10  # dep/gemini/constants.hpp
+
+
+def partition_offsets_from_out_degree(out_degree_raw, n_edges, partitions):
+    """The reference's vertex-chunk partitioner (core/graph.hpp:1185-1211) from the RAW (un-clamped) out-degree
+    array: greedy prefix over out_degree + alpha, alpha = 12*(P+1); cut rounded down to PAGESIZE.  Pure host
+    arithmetic on V integers (numpy); same result as nts_host_partition_offsets."""
+    deg = np.asarray(out_degree_raw, dtype=np.int64)
+    V = int(deg.shape[0])
+    P = int(partitions)
+    alpha = 12 * (P + 1)
+    prefix = np.concatenate([[0], np.cumsum(deg + alpha)])
+    off = np.zeros(P + 1, dtype=np.uint32)
+    remained = int(n_edges) + V * alpha
+    for i in range(P):
+        left = P - i
+        start = int(off[i])
+        if left == 1:
+            off[i + 1] = V
+        else:
+            expected = remained // left
+            v_i = int(np.searchsorted(prefix[1:], prefix[start] + expected, side="right"))
+            v_i = max(min(v_i, V - 1), start)
+            off[i + 1] = (v_i // PAGESIZE) * PAGESIZE
+        remained -= int(prefix[int(off[i + 1])] - prefix[start])
+    return off
+
+
 class HostGraph:
     """A packed binary edge list ({u32 src, u32 dst}, dep/gemini/type.hpp:100-106) plus the global
     artefacts every rank derives from it: clamped degrees and the partition offsets."""

@@ -32,6 +32,39 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+class KernelTimer:
+    """Optional CUDA-event bracket around every aggregation launch (bench.py's live roofline measurement).
+    Events are recorded on the stream the kernel is launched on; nothing is synchronised until `summary()`."""
+
+    def __init__(self):
+        self.records = []  # (tag, F, edges, rows, start, stop)
+
+    def bracket(self, tag, F, edges, rows):
+        start = torch.cuda.Event(enable_timing=True)
+        stop = torch.cuda.Event(enable_timing=True)
+        self.records.append((tag, int(F), int(edges), int(rows), start, stop))
+        return start, stop
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, F, edges, rows, a, b in self.records:
+            d = out.setdefault((tag, F), {"calls": 0, "ms": 0.0, "edges": 0, "rows": 0})
+            d["calls"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["edges"] += edges
+            d["rows"] += rows
+        return out
+
+
+_timer = None
+
+
+def set_kernel_timer(timer):
+    global _timer
+    _timer = timer
+
+
 def segment_gather_sum(out, x, weight, indices, offsets, index_base, n_rows, n_edges):
     """out[r,:] += sum_e x[indices[e]-index_base,:] * weight[e]  (nts_segment_gather_sum)."""
     _lib.call("nts_segment_gather_sum", _ptr(x), _ptr(out), _ptr(weight), _ptr(indices), _ptr(offsets),
@@ -41,19 +74,29 @@ def segment_gather_sum(out, x, weight, indices, offsets, index_base, n_rows, n_e
 
 def gather_by_dst_from_src(chunk, out, x, with_weight=True):
     """NtsScheduler::GatherByDstFromSrc (core/NtsScheduler.hpp:151-191) on one chunk."""
+    ev = _timer.bracket("fwd", x.shape[1], chunk.edge_size, chunk.batch_size_forward) if _timer else None
+    if ev:
+        ev[0].record()
     _lib.call("nts_gather_by_dst_from_src", _ptr(x), _ptr(out), _ptr(chunk.edge_weight_forward_gpu),
               _ptr(chunk.row_indices_gpu), _ptr(chunk.column_offset_gpu), chunk.src_range[0], chunk.src_range[1],
               chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_forward,
               int(x.shape[1]), 1 if with_weight else 0, _stream())
+    if ev:
+        ev[1].record()
     return out
 
 
 def gather_by_src_from_dst(chunk, out, grad, with_weight=True):
     """NtsScheduler::GatherBySrcFromDst (core/NtsScheduler.hpp:257-293) on one chunk."""
+    ev = _timer.bracket("bwd", grad.shape[1], chunk.edge_size, chunk.batch_size_backward) if _timer else None
+    if ev:
+        ev[0].record()
     _lib.call("nts_gather_by_src_from_dst", _ptr(grad), _ptr(out), _ptr(chunk.edge_weight_backward_gpu),
               _ptr(chunk.row_offset_gpu), _ptr(chunk.column_indices_gpu), chunk.src_range[0], chunk.src_range[1],
               chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_backward,
               int(grad.shape[1]), 1 if with_weight else 0, _stream())
+    if ev:
+        ev[1].record()
     return out
 
 

@@ -1,0 +1,160 @@
+"""Callers of the hot path, mirrored from the reference so the path can be driven and timed end to end:
+
+  * `Parameter`  <-> core/NtsScheduler.hpp:639-791 (weight, L2-regularised Adam with the reference's bias-correction
+                     folded into alpha by `next()`, gradient SUM-allreduce - NCCL instead of MPI on host copies)
+  * `GCNImpl`    <-> toolkits/GCN.hpp (2-layer GCN: aggregate -> X.W -> relu / log_softmax, nll loss on the train
+                     mask, tape backward, Adam) and toolkits/GCN_EAGER_single.hpp for the single-GPU op.
+
+Dense NN work (mm, relu, log_softmax, nll_loss, Adam element-wise) stays on torch/cuBLAS exactly as in the
+reference (libtorch); the aggregation goes through libnts_b200."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+from .context import NtsContext
+from . import ops
+
+
+class Parameter:
+    def __init__(self, w, h, alpha, beta1, beta2, epsilon, weight_decay, device=None, generator=None):
+        scale = math.sqrt(6.0 / (w + h))
+        W = (2 * scale) * torch.rand((w, h), dtype=torch.float32, generator=generator) - scale
+        self.W = W.to(device).requires_grad_(True)
+        self.M = torch.zeros((w, h), dtype=torch.float32, device=device)
+        self.V = torch.zeros((w, h), dtype=torch.float32, device=device)
+        self.W_gradient = None
+        self.alpha = alpha
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.alpha_t, self.beta1_t, self.beta2_t = alpha, beta1, beta2
+        self.weight_decay = weight_decay
+        self.curr_epoch = 0
+        self.decay_rate, self.decay_epoch = 1, -1
+
+    def init_parameter(self):
+        """Network_simple::broadcast from rank 0 (comm/network.h:205-211)."""
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.W.data, src=0)
+
+    def set_decay(self, decay_rate, decay_epoch):
+        # the reference stores both in `int` members (NtsScheduler.hpp:663-664): 0.97 truncates to 0
+        self.decay_rate, self.decay_epoch = int(decay_rate), int(decay_epoch)
+
+    def all_reduce_to_gradient(self, grad):
+        """SUM (not mean) over ranks, NtsScheduler.hpp:719-722 -> comm/network.h:198-203."""
+        self.W_gradient = grad.detach().clone()
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.W_gradient, op=dist.ReduceOp.SUM)
+
+    def next(self):
+        """NtsScheduler.hpp:727-736."""
+        if self.decay_epoch != -1 and self.curr_epoch != 0 and self.curr_epoch % self.decay_epoch == 0:
+            self.alpha_t *= self.decay_rate
+        self.alpha = self.alpha_t * math.sqrt(1 - self.beta2) / (1 - self.beta1)
+        self.beta1 *= self.beta1_t
+        self.beta2 *= self.beta2_t
+        self.curr_epoch += 1
+
+    def forward(self, x):
+        return x.mm(self.W)
+
+    def learn_with_decay_Adam(self):
+        """learnC2G_with_decay_Adam, NtsScheduler.hpp:774-781."""
+        with torch.no_grad():
+            W_g = self.W * self.weight_decay + self.W_gradient
+            self.M = self.beta1 * self.M + (1 - self.beta1) * W_g
+            self.V = self.beta2 * self.V + (1 - self.beta2) * W_g * W_g
+            self.W -= self.alpha * self.M / (torch.sqrt(self.V) + self.epsilon)
+
+    def zero_grad(self):
+        self.W.grad = None
+
+
+class GCNImpl:
+    """toolkits/GCN.hpp:33-354.  `layers` = LAYERS of the cfg, e.g. [602, 128, 41]."""
+
+    def __init__(self, partitioned_graph, layers, features, labels, mask, learn_rate=0.01, weight_decay=0.0001,
+                 decay_rate=0.97, decay_epoch=100, drop_rate=0.5, op_class=None, op_kwargs=None, seed=0):
+        self.pg = partitioned_graph
+        self.layers = list(layers)
+        self.device = features.device
+        self.drop_rate = drop_rate
+        self.ctx = NtsContext()
+        gen = torch.Generator().manual_seed(seed)
+        self.P = []
+        for i in range(len(self.layers) - 1):
+            p = Parameter(self.layers[i], self.layers[i + 1], learn_rate, 0.9, 0.999, 1e-9, weight_decay,
+                          device=self.device, generator=gen)
+            p.init_parameter()
+            p.set_decay(decay_rate, decay_epoch)
+            self.P.append(p)
+        self.L_GT = labels.to(self.device)
+        self.MASK = mask.to(self.device)
+        self.train_rows = (self.MASK == 0).nonzero().view(-1)
+        self.X = [None] * len(self.layers)
+        self.X[0] = features.requires_grad_(True)
+        if op_class is None:
+            op_class = ops.ForwardSingleGPUfuseOp if partitioned_graph.partitions == 1 else ops.ForwardGPUfuseOp
+        self.op_class = op_class
+        self.op_kwargs = op_kwargs or {}
+        self.loss = None
+        self.epoch = 0
+
+    def vertexForward(self, a, x, layer):
+        """GCN.hpp:183-196."""
+        if layer < len(self.layers) - 2:
+            return torch.relu(self.P[layer].forward(a))
+        return self.P[layer].forward(a).log_softmax(1)
+
+    def Forward(self):
+        """GCN.hpp:217-235."""
+        for i in range(len(self.layers) - 1):
+            x_i = self.X[i]
+            if i != 0 and self.drop_rate > 0:
+                # the reference drops in place (GCN.hpp:221-223); out of place + chaining onto the NN segment
+                # keeps torch's autograd version check happy and is numerically the same operation
+                dropped = torch.nn.functional.dropout(x_i, self.drop_rate, training=True)
+                self.ctx.appendNNOp(x_i, dropped)
+                x_i = dropped
+            x_i = x_i.contiguous()
+            y_i = self.ctx.runGraphOp(self.op_class, self.pg, None, x_i, **self.op_kwargs)
+            self.X[i + 1] = self.ctx.runVertexForward(lambda n, v, _l=i: self.vertexForward(n, v, _l), y_i, x_i)
+
+    def Loss(self):
+        """GCN.hpp:198-207: nll_loss over the local train rows (mean)."""
+        a = self.X[-1]
+        self.loss = torch.nn.functional.nll_loss(a.index_select(0, self.train_rows),
+                                                 self.L_GT.index_select(0, self.train_rows))
+        self.ctx.appendNNOp(a, self.loss)
+
+    def Update(self):
+        """GCN.hpp:209-215."""
+        for p in self.P:
+            p.all_reduce_to_gradient(p.W.grad)
+            p.learn_with_decay_Adam()
+            p.next()
+
+    def Test(self, s):
+        """GCN.hpp:150-181: accuracy over mask == s, summed over ranks."""
+        sel = self.MASK == s
+        correct = (self.X[-1].argmax(1) == self.L_GT)[sel].sum()
+        total = sel.sum()
+        pair = torch.stack([correct, total]).to(torch.int64)
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(pair)
+        return pair
+
+    def run_epoch(self, test=False):
+        """One iteration of GCN.hpp:244-262."""
+        if self.epoch != 0:
+            for p in self.P:
+                p.zero_grad()
+        self.Forward()
+        acc = [self.Test(s) for s in (0, 1, 2)] if test else None
+        self.Loss()
+        self.ctx.self_backward(True)
+        self.Update()
+        self.epoch += 1
+        return self.loss, acc

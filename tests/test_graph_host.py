@@ -63,3 +63,10 @@ def test_empty_graph_and_single_vertex():
     assert np.array_equal(pg.graph_chunks[0].column_offset, np.zeros(6, dtype=np.uint32))
     out_d, in_d = hg.degrees()
     assert (out_d == 1).all() and (in_d == 1).all()
+
+
+def test_partition_offsets_from_degrees_matches_reference(golden):
+    from neutronstarlite_b200.graph import partition_offsets_from_out_degree
+    g = golden
+    raw = np.bincount(g.edges[:, 0], minlength=g.V)
+    assert np.array_equal(partition_offsets_from_out_degree(raw, g.E, g.P), g.partition_offset)
