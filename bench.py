@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline runs on E/div edges")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA kernels")
+    ap.add_argument("--zipf-s", type=float, default=1.0, help="endpoint skew (1.0 = SURVEY 8d power law, 0 = uniform)")
     return ap.parse_args()
 
 
@@ -227,7 +229,7 @@ def main():
     _lib.call("nts_aggregate_set_variant", args.variant, args.edges_per_warp)
 
     # graph: every rank generates the same edge list (same seed), keeps only what it owns
-    src, dst = synth.zipf_edges(V, E_rand, dev)
+    src, dst = synth.zipf_edges(V, E_rand, dev, s=args.zipf_s)
     out_raw = torch.bincount(src, minlength=V)
     out_deg = out_raw.clamp(min=1)
     in_deg = torch.bincount(dst, minlength=V).clamp_(min=1)
@@ -336,6 +338,12 @@ def main():
                                       "gedges_per_s": d["edges"] / (d["ms"] * 1e-3) / 1e9}
                for (tag, F), d in ksum.items()}
 
+    ref_gpu = None
+    if world == 1 and not args.no_ref_gpu:
+        try:
+            ref_gpu = reference_gpu_kernels(pg, feats, layers, torch)
+        except Exception as exc:  # baseline only: never fail the bench because of it
+            ref_gpu = {"error": repr(exc)}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -357,15 +365,64 @@ def main():
                        if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (features %.0f MB, graph arrays %.0f MB per rank)" % (
                            feats.numel() * 4 / 1e6, pg.owned_edges * 16 / 1e6),
-                       "drop_rate": args.drop_rate, "kernel_variant": args.variant or 1},
+                       "drop_rate": args.drop_rate, "kernel_variant": args.variant or 2, "zipf_s": args.zipf_s},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "kernels": kernels, "clocks": clocks,
+            "kernels": kernels, "reference_gpu_kernels": ref_gpu, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def reference_gpu_kernels(pg, feats, layers, torch):
+    """Time the UNMODIFIED reference CUDA kernels (cuda/ntsCUDAFuseKernel.cuh, compiled for sm_100a into
+    oracle/_ref/libnts_refcuda.so) on the same chunk and inputs: 1 warm-up + 2 timed launches per width, CUDA events
+    on the reference's own stream.  Also cross-checks their output against ours.  Bench-only baseline."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libnts_refcuda.so")
+    if not os.path.exists(so):
+        return None
+    from neutronstarlite_b200 import ops
+    ref = C.CDLL(so)
+    ref.refcuda_stream_create.restype = C.c_void_p
+    ref.refcuda_stream_handle.restype = C.c_void_p
+    ref.refcuda_stream_handle.argtypes = [C.c_void_p]
+    ref.refcuda_stream_sync.argtypes = [C.c_void_p]
+    ref.refcuda_gather_by_dst_from_src.argtypes = [C.c_void_p] * 6 + [C.c_uint] * 7 + [C.c_int, C.c_int]
+    ref.refcuda_gather_by_dst_from_src.restype = None
+    cs = ref.refcuda_stream_create()
+    ext = torch.cuda.ExternalStream(ref.refcuda_stream_handle(cs))
+    c = pg.graph_chunks[0]
+    out = {}
+    for F, optim in ((layers[0], 0), (layers[1], 0), (layers[1], 1)):
+        x = feats[:, :F].contiguous() if F <= feats.shape[1] else torch.rand((feats.shape[0], F), device=feats.device)
+        y = torch.zeros((c.batch_size_forward, F), device=feats.device)
+        torch.cuda.synchronize()
+        times = []
+        for it in range(3):
+            y.zero_()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(ext)
+            ref.refcuda_gather_by_dst_from_src(cs, x.data_ptr(), y.data_ptr(), c.edge_weight_forward_gpu.data_ptr(),
+                                               c.row_indices_gpu.data_ptr(), c.column_offset_gpu.data_ptr(),
+                                               c.src_range[0], c.src_range[1], c.dst_range[0], c.dst_range[1],
+                                               c.edge_size, c.batch_size_forward, F, 1, optim)
+            b.record(ext)
+            ref.refcuda_stream_sync(cs)
+            torch.cuda.synchronize()
+            if it > 0:
+                times.append(a.elapsed_time(b))
+        mine = torch.zeros_like(y)
+        ops.gather_by_dst_from_src(c, mine, x)
+        torch.cuda.synchronize()
+        err = float(((mine - y).abs().max() / y.abs().max().clamp(min=1e-30)).item())
+        key = "F%d_%s" % (F, "optim_nts" if optim else "plain")
+        out[key] = {"avg_ms": sum(times) / len(times), "max_rel_diff_vs_ours": err,
+                    "gedges_per_s": c.edge_size / (sum(times) / len(times) * 1e-3) / 1e9}
+    return out
 
 
 def _workload_name(name, V, E, layers):

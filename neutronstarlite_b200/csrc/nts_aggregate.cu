@@ -132,9 +132,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   const uint32_t warp_in_block = threadIdx.x >> 5;
   const uint32_t nvec = F / VEC;
 
-  // quantum / tile owned by this warp.  In BULK mode all warps of a CTA share one column tile range
-  // layout: consecutive warps = consecutive tiles of the same quantum, so one CTA covers
-  // kWarpsPerBlock/tiles... (kept simple: CTA covers quanta [cta_q0, cta_q0 + quanta_per_cta)).
+  // quantum / tile owned by this warp: consecutive warps = consecutive column tiles of the same quantum, so the
+  // warps of one CTA share a contiguous edge span (one bulk copy stages its indices and weights for all of them)
   const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp_in_block;
   const uint32_t tile = (uint32_t)(gwarp % tiles);
   const uint64_t q = gwarp / tiles;
@@ -386,7 +385,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
       Q >>= 1;
   }
   Q = (Q + 31u) & ~31u;
-  int variant = g_variant == 0 ? 1 : g_variant;
+  int variant = g_variant == 0 ? 2 : g_variant; // measured on B200: bulk-staged indices are ~20% faster
   bool bulk = variant == 2;
   // the bulk copies need 16-byte aligned index/weight arrays (cudaMalloc gives 256)
   if (bulk && !(aligned_to(idx, 16) && (!w || aligned_to(w, 16)))) {
