@@ -13,7 +13,8 @@
 //     (cuda/ntsCUDAFuseKernel.cuh:203-204,264,381,441); here plain and _Optim entry points run the same kernel;
 //   * the reference GPU edge softmax has no max subtraction (cuda/ntsCUDADistKernel.cuh:192); ours matches the
 //     CPU operator (core/ntsDistCPUGraphOp.hpp:463) instead;
-//   * Gather_By_Dst_From_Message is declared but never defined in the reference; it is not declared here.
+//   * Gather_By_Dst_From_Message is declared but never defined in the reference (a link error if it were ever
+//     used); here it is defined with the semantics of the kernel it was meant to launch.
 #pragma once
 
 #include <cstdio>
@@ -21,8 +22,12 @@
 
 #include "nts_b200.h"
 
-#if !defined(__CUDACC__) && !defined(CUDART_VERSION) && !defined(__DRIVER_TYPES_H__)
-// Reference headers only need the stream type by name (ntsCUDA.hpp:102).
+#if defined(CUDA_ENABLE) && CUDA_ENABLE
+// the reference header pulls the CUDA runtime in (cuda/ntsCUDA.hpp:10-12) and comm/network.cpp:56,87 calls
+// cudaFreeHost directly, so a drop-in has to do the same
+#include "cuda_runtime.h"
+#elif !defined(__CUDACC__) && !defined(CUDART_VERSION) && !defined(__DRIVER_TYPES_H__)
+// without the toolkit headers only the stream type is needed, by name (ntsCUDA.hpp:102)
 struct CUstream_st;
 typedef struct CUstream_st *cudaStream_t;
 #endif
@@ -275,6 +280,20 @@ public:
     nts_compat::must(nts_edge_softmax_backward(msg_input_grad, msg_output_grad, msg_cached, row_indices,
                                                column_offset, batch_size, feature_size, stream),
                      "Edge_Softmax_Backward_Block");
+  }
+  // Declared by the reference (ntsCUDA.hpp:186-192) and called from NtsScheduler::GatherByDstFromMessage
+  // (core/NtsScheduler.hpp:192-211) but never defined in cuda/ntsCUDAGraphOP.cu; the intended kernel
+  // (aggregate_kernel_from_message_without_weight_sum, cuda/ntsCUDAFuseKernel.cuh:562-577) is
+  // output[d,:] += sum_{e->d} message[e,:] with (src, dst) = (row_indices, column_offset) - our Gather_Msg_to_Dst.
+  void Gather_By_Dst_From_Message(float *input, float *output, VertexId_CUDA *src, VertexId_CUDA *dst,
+                                  VertexId_CUDA src_start, VertexId_CUDA src_end, VertexId_CUDA dst_start,
+                                  VertexId_CUDA dst_end, VertexId_CUDA edges, VertexId_CUDA batch_size,
+                                  VertexId_CUDA feature_size, bool with_weight = false,
+                                  bool tensor_weight = false) {
+    (void)src_start; (void)src_end; (void)dst_start; (void)dst_end; (void)edges; (void)with_weight;
+    (void)tensor_weight;
+    nts_compat::must(nts_gather_msg_to_dst(output, input, src, dst, batch_size, feature_size, stream),
+                     "Gather_By_Dst_From_Message");
   }
   void Scatter_Grad_Back_To_Message(float *input, float *message_grad, VertexId_CUDA *row_indices,
                                     VertexId_CUDA *column_offset, VertexId_CUDA src_start, VertexId_CUDA src_end,

@@ -120,8 +120,9 @@ constexpr int kWarpsPerBlock = 8;
 // K    : vector chunks per lane per column tile (a tile covers K*32*VEC floats)
 // U    : edges loaded before the FMAs start (memory-level parallelism = U*K loads per lane)
 // BULK : stage index/weight tiles with cp.async.bulk + mbarrier (variant 2)
-template <int VEC, int K, int U, bool BULK>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// MINB : minimum resident CTAs per SM handed to __launch_bounds__ (register cap = 65536 / (256*MINB))
+template <int VEC, int K, int U, bool BULK, int MINB = 1>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     segment_gather_sum_kernel(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ w,
                               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
                               const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
@@ -337,7 +338,7 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F) {
   return s;
 }
 
-template <int VEC, int K, int U>
+template <int VEC, int K, int U, int MINB = 1>
 static int launch_shape(bool bulk, const float *in, float *out, const float *w, const uint32_t *idx,
                         const uint32_t *off, const uint32_t *slot_of, uint32_t base, uint32_t n_rows,
                         uint64_t n_edges, uint32_t F, uint32_t Q, uint32_t tiles, cudaStream_t st) {
@@ -350,14 +351,14 @@ static int launch_shape(bool bulk, const float *in, float *out, const float *w, 
   if (bulk) {
     size_t span_cap = (size_t)kWarpsPerBlock * Q + 8;
     size_t smem = 16 + 2 * span_cap * 4;
-    auto kern = segment_gather_sum_kernel<VEC, K, U, true>;
+    auto kern = segment_gather_sum_kernel<VEC, K, U, true, MINB>;
     NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_last_smem = (int)smem;
     kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F,
                                                               Q, tiles);
   } else {
     g_last_smem = 0;
-    segment_gather_sum_kernel<VEC, K, U, false>
+    segment_gather_sum_kernel<VEC, K, U, false, MINB>
         <<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q,
                                                            tiles);
   }
@@ -393,6 +394,26 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
     variant = 1;
   }
   g_last_variant = variant;
+  // experiment hook: NTS_AGG_TUNE="U,MINB" picks another (U, occupancy) point for the two headline shapes
+  if (const char *tune = getenv("NTS_AGG_TUNE")) {
+    int tu = 0, tb = 0;
+    if (sscanf(tune, "%d,%d", &tu, &tb) == 2) {
+#define NTS_TUNE_CASE(V_, K_, U_, B_)                                                                        \
+  if (s.vec == V_ && s.k == K_ && tu == U_ && tb == B_)                                                       \
+    return launch_shape<V_, K_, U_, B_>(bulk, in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, s.tiles, st);
+      NTS_TUNE_CASE(2, 5, 2, 4)
+      NTS_TUNE_CASE(2, 5, 2, 3)
+      NTS_TUNE_CASE(2, 5, 4, 3)
+      NTS_TUNE_CASE(2, 5, 8, 1)
+      NTS_TUNE_CASE(2, 5, 1, 4)
+      NTS_TUNE_CASE(4, 1, 8, 4)
+      NTS_TUNE_CASE(4, 1, 4, 6)
+      NTS_TUNE_CASE(4, 1, 8, 6)
+      NTS_TUNE_CASE(4, 1, 16, 2)
+      NTS_TUNE_CASE(4, 1, 16, 3)
+#undef NTS_TUNE_CASE
+    }
+  }
   NTS_SHAPE_CASE(4, 1, 8)
   NTS_SHAPE_CASE(4, 2, 4)
   NTS_SHAPE_CASE(4, 3, 2)

@@ -1,0 +1,86 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY - run the reference's OWN host code on our kernels (the drop-in proof).
+
+`oracle/_ref/nts_dropin_main` is the reference's `toolkits/main.cpp` (every GPU toolkit: GCN.hpp, GCN_EAGER*.hpp,
+GAT_GPU_DIST.hpp, GIN_GPU.hpp, COMMNET_GPU.hpp, test_getdepneighbor_gpu.hpp) compiled unchanged with -DCUDA_ENABLE=1
+against include/nts_dropin (our shadow of cuda/ntsCUDA.hpp) and linked with libnts_b200.so instead of the reference's
+cuda_propagate library (oracle/Makefile target `dropin`).  This script runs it on the reference's Cora fixture for a
+list of ALGORITHM values on the GPU box (single rank: the MPI stand-in is in-process) and, for comparison, the CPU
+reference binary on the same cfg.  Prints one JSON object per algorithm with the parsed per-epoch losses and final
+accuracies.
+
+    python oracle/run_dropin.py [--epochs 30] [--algos GCNEAGERSINGLE,GCN,GATGPUDIST,test_getdep]
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+
+CFG = """ALGORITHM:{algo}
+VERTICES:2708
+LAYERS:{layers}
+EPOCHS:{epochs}
+EDGE_FILE:{data}/cora.2708.edge.self
+FEATURE_FILE:{data}/cora.featuretable
+LABEL_FILE:{data}/cora.labeltable
+MASK_FILE:{data}/cora.mask
+PROC_OVERLAP:0
+PROC_LOCAL:0
+PROC_CUDA:1
+PROC_REP:0
+LOCK_FREE:1
+LEARN_RATE:0.01
+WEIGHT_DECAY:0.0001
+DECAY_RATE:0.97
+DECAY_EPOCH:100
+DROP_RATE:0.0
+"""
+
+
+def run(binary, algo, epochs, layers="1433-128-7", timeout=600):
+    with tempfile.TemporaryDirectory() as d:
+        cfg = os.path.join(d, "c.cfg")
+        open(cfg, "w").write(CFG.format(algo=algo, layers=layers, epochs=epochs, data=os.path.join(REF, "data")))
+        env = dict(os.environ)
+        env.setdefault("NTS_THREADS", "8")
+        env["OMP_NUM_THREADS"] = env["NTS_THREADS"]
+        p = subprocess.run([binary, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
+                           timeout=timeout)
+    out = p.stdout
+    losses = [float(x) for x in re.findall(r"Epoch\[\d+\]:loss\s+([-0-9.eE+]+)", out)]
+    accs = re.findall(r"(Train|Eval|Test)\s+ACC:\s+([0-9.]+)", out)
+    last = {}
+    for k, v in accs:
+        last[k.lower()] = float(v)
+    passed = re.findall(r"(\d+) is passed|passed", out)
+    return {"algo": algo, "rc": p.returncode, "epochs": len(losses), "loss_first": losses[0] if losses else None,
+            "loss_last": losses[-1] if losses else None, "acc": last, "tail": out[-600:] if p.returncode else "",
+            "raw_passed_lines": [ln for ln in out.splitlines() if "pass" in ln.lower()][:12]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--epochs", type=int, default=30)
+    ap.add_argument("--algos", default="GCNEAGERSINGLE,GCN,GATGPUDIST,test_getdep")
+    a = ap.parse_args()
+    res = {}
+    cpu = os.path.join(REF, "nts_ref_main")
+    gpu = os.path.join(REF, "nts_dropin_main")
+    res["cpu_reference_GCNCPU"] = run(cpu, "GCNCPU", a.epochs)
+    for algo in a.algos.split(","):
+        try:
+            res["dropin_" + algo] = run(gpu, algo, a.epochs)
+        except subprocess.TimeoutExpired:
+            res["dropin_" + algo] = {"algo": algo, "rc": "timeout"}
+    print(json.dumps(res, indent=1))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Kernel-level sweep of the aggregation kernel on the Reddit-shaped graph (one graph build, many configurations).
+Prints one JSON line per configuration: avg ms of the F=602 and F=128 forward launches (CUDA events, 5 launches
+after 2 warm-ups).  Usage: python tools/tune_aggregate.py [--zipf-s 1.0] [--configs "v,Q,U,B;..."]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+from neutronstarlite_b200 import _lib, ops, synth
+from neutronstarlite_b200.graph import PartitionedGraph
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--zipf-s", type=float, default=1.0)
+    ap.add_argument("--workload", default="reddit")
+    ap.add_argument("--configs", default="1,0,0,0;2,0,0,0;2,128,0,0;2,512,0,0;2,1024,0,0;2,0,2,4;2,0,2,3;2,0,4,3;2,0,8,1;"
+                                         "2,0,1,4;2,0,8,4;2,0,4,6;2,0,8,6;2,0,16,2;2,0,16,3")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    V, E_rand, layers = synth.WORKLOADS[a.workload]
+    src, dst = synth.zipf_edges(V, E_rand, dev, s=a.zipf_s)
+    pg = PartitionedGraph.from_device_edges(src, dst, V)
+    del src, dst
+    c = pg.graph_chunks[0]
+    xs = {F: torch.rand((V, F), device=dev) * 2 - 1 for F in (layers[0], layers[1])}
+    ys = {F: torch.zeros((V, F), device=dev) for F in xs}
+    for cfg in a.configs.split(";"):
+        v, q, u, b = (int(t) for t in cfg.split(","))
+        _lib.call("nts_aggregate_set_variant", v, q)
+        if u:
+            os.environ["NTS_AGG_TUNE"] = "%d,%d" % (u, b)
+        else:
+            os.environ.pop("NTS_AGG_TUNE", None)
+        res = {"variant": v, "Q": q, "U": u, "minb": b}
+        for F in xs:
+            for _ in range(2):
+                ops.gather_by_dst_from_src(c, ys[F], xs[F])
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(5):
+                ops.gather_by_dst_from_src(c, ys[F], xs[F])
+            a1.record()
+            torch.cuda.synchronize()
+            res["F%d_ms" % F] = a0.elapsed_time(a1) / 5
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()
