@@ -126,18 +126,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     segment_gather_sum_kernel(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ w,
                               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
                               const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
-                              uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles) {
+                              uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
+                              uint32_t tile_major) {
   using V = typename Vec<VEC>::type;
   const uint32_t n_edges = (uint32_t)n_edges64;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp_in_block = threadIdx.x >> 5;
   const uint32_t nvec = F / VEC;
 
-  // quantum / tile owned by this warp: consecutive warps = consecutive column tiles of the same quantum, so the
-  // warps of one CTA share a contiguous edge span (one bulk copy stages its indices and weights for all of them)
+  // quantum / column tile owned by this warp.
+  //   interleaved (tile_major = 0): consecutive warps = the column tiles of one quantum (they share index loads)
+  //   tile-major  (tile_major = 1): all quanta of tile 0 first, then tile 1, ...: at any moment the CTAs in flight
+  //     touch one column slab of the feature matrix, which is sized to stay resident in the 126 MB L2.
+  //     Warps per tile are padded to a multiple of the CTA size so a CTA never straddles two tiles.
   const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp_in_block;
-  const uint32_t tile = (uint32_t)(gwarp % tiles);
-  const uint64_t q = gwarp / tiles;
+  const uint64_t n_quanta = (n_edges64 + Q - 1) / Q;
+  const uint64_t wpt = (n_quanta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock;
+  const uint32_t tile = tile_major ? (uint32_t)(gwarp / wpt) : (uint32_t)(gwarp % tiles);
+  const uint64_t q = tile_major ? gwarp % wpt : gwarp / tiles;
   const uint64_t e0_64 = q * (uint64_t)Q;
 
   // BULK staging buffers: indices+weights of every edge this CTA touches
@@ -148,8 +154,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   uint32_t bulk_bytes = 0;
   if constexpr (BULK) {
     // CTA edge span: quanta of warps 0..kWarpsPerBlock-1
-    const uint64_t first_q = ((uint64_t)blockIdx.x * kWarpsPerBlock) / tiles;
-    const uint64_t last_q = ((uint64_t)blockIdx.x * kWarpsPerBlock + kWarpsPerBlock - 1) / tiles;
+    const uint64_t cta_w0 = (uint64_t)blockIdx.x * kWarpsPerBlock;
+    const uint64_t first_q = tile_major ? cta_w0 % wpt : cta_w0 / tiles;
+    const uint64_t last_q = tile_major ? first_q + kWarpsPerBlock - 1 : (cta_w0 + kWarpsPerBlock - 1) / tiles;
     uint64_t ce0 = first_q * (uint64_t)Q;
     uint64_t ce1 = (last_q + 1) * (uint64_t)Q;
     if (ce1 > n_edges)
@@ -189,11 +196,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   const uint32_t e1 = (e0_64 + Q < n_edges64) ? e0 + Q : n_edges;
 
   // column tile handled by this warp
-  const uint32_t c0 = tile * (K * 32) + lane; // first vector column of this lane
+  const uint32_t c0 = tile * tile_vecs + lane; // first vector column of this lane
   bool act[K];
 #pragma unroll
   for (int k = 0; k < K; k++)
-    act[k] = (c0 + k * 32) < nvec;
+    act[k] = (k * 32 + lane) < tile_vecs && (c0 + k * 32) < nvec;
 
   // first row of the quantum (overlaps with the bulk copy in flight)
   uint32_t row = find_row(off, n_rows, e0);
@@ -311,11 +318,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 
 // ---- host-side dispatch ---------------------------------------------------------------------------------
 struct LaunchShape {
-  int vec, k, u;
-  uint32_t tiles;
+  int vec, k, u, minb;
+  uint32_t tiles, tile_vecs, tile_major;
 };
 
-static LaunchShape pick_shape(const float *in, const float *out, uint32_t F) {
+static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uint32_t n_src_rows_hint) {
   LaunchShape s;
   bool a16 = aligned_to(in, 16) && aligned_to(out, 16);
   bool a8 = aligned_to(in, 8) && aligned_to(out, 8);
@@ -325,26 +332,55 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F) {
     s.vec = 2;
   else
     s.vec = 1;
-  uint32_t nvec = F / s.vec;
-  uint32_t chunks = (nvec + 31) / 32;
-  // chunks per lane per tile: balance tiles so the last one is not nearly empty
+  const uint32_t nvec = F / s.vec;
+  const uint32_t chunks = (nvec + 31) / 32;
   const uint32_t kmax = (s.vec == 4) ? 4 : 5;
   s.tiles = (chunks + kmax - 1) / kmax;
-  s.k = (int)((chunks + s.tiles - 1) / s.tiles);
-  s.tiles = (chunks + s.k - 1) / s.k;
-  // loads in flight per lane ~ 32-40 floats
+  s.tile_major = 0;
+  (void)n_src_rows_hint;
+  // experiment / tuning hook: NTS_AGG_TILES="tiles,tile_major"
+  if (const char *e = getenv("NTS_AGG_TILES")) {
+    int t = 0, m = 0;
+    if (sscanf(e, "%d,%d", &t, &m) == 2 && t >= 1 && (uint32_t)t <= chunks && (chunks + t - 1) / t <= kmax) {
+      s.tiles = (uint32_t)t;
+      s.tile_major = m ? 1u : 0u;
+    }
+  }
+  s.tile_vecs = (nvec + s.tiles - 1) / s.tiles;
+  s.k = (int)((s.tile_vecs + 31) / 32);
+  s.tiles = (nvec + s.tile_vecs - 1) / s.tile_vecs;
+  // (U, min CTAs/SM): measured on B200 for the headline shapes (profiles/tune_r1_*.jsonl), generic rule otherwise
+  s.minb = 1;
   int budget = 40 / (s.k * s.vec);
   s.u = budget >= 8 ? 8 : (budget >= 4 ? 4 : 2);
+  if (s.vec == 2 && s.k == 5) {
+    s.u = 2;
+    s.minb = 3;
+  } else if (s.vec == 4 && s.k == 1) {
+    s.u = 8;
+    s.minb = 3;
+  }
+  if (const char *tune = getenv("NTS_AGG_TUNE")) {
+    int tu = 0, tb = 0;
+    if (sscanf(tune, "%d,%d", &tu, &tb) == 2) {
+      s.u = tu;
+      s.minb = tb;
+    }
+  }
   return s;
 }
 
-template <int VEC, int K, int U, int MINB = 1>
-static int launch_shape(bool bulk, const float *in, float *out, const float *w, const uint32_t *idx,
-                        const uint32_t *off, const uint32_t *slot_of, uint32_t base, uint32_t n_rows,
-                        uint64_t n_edges, uint32_t F, uint32_t Q, uint32_t tiles, cudaStream_t st) {
-  uint64_t quanta = (n_edges + Q - 1) / Q;
-  uint64_t warps = quanta * tiles;
-  uint64_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
+template <int VEC, int K, int U, int MINB>
+static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float *out, const float *w,
+                        const uint32_t *idx, const uint32_t *off, const uint32_t *slot_of, uint32_t base,
+                        uint32_t n_rows, uint64_t n_edges, uint32_t F, uint32_t Q, cudaStream_t st) {
+  const uint64_t quanta = (n_edges + Q - 1) / Q;
+  uint64_t warps;
+  if (sh.tile_major)
+    warps = (quanta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock * sh.tiles;
+  else
+    warps = quanta * sh.tiles;
+  const uint64_t blocks = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
   NTS_ARG_CHECK(blocks <= 0x7fffffffull, "aggregation grid too large");
   g_last_grid = (int)blocks;
   g_last_block = kWarpsPerBlock * 32;
@@ -355,20 +391,19 @@ static int launch_shape(bool bulk, const float *in, float *out, const float *w, 
     NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_last_smem = (int)smem;
     kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F,
-                                                              Q, tiles);
+                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major);
   } else {
     g_last_smem = 0;
-    segment_gather_sum_kernel<VEC, K, U, false, MINB>
-        <<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q,
-                                                           tiles);
+    segment_gather_sum_kernel<VEC, K, U, false, MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+        in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major);
   }
   NTS_LAUNCH_CHECK();
   return 0;
 }
 
-#define NTS_SHAPE_CASE(V_, K_, U_)                                                                            \
-  if (s.vec == V_ && s.k == K_ && s.u == U_)                                                                   \
-    return launch_shape<V_, K_, U_>(bulk, in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, s.tiles, st);
+#define NTS_CASE(V_, K_, U_, B_)                                                                               \
+  if (s.vec == V_ && s.k == K_ && s.u == U_ && s.minb == B_)                                                    \
+    return launch_shape<V_, K_, U_, B_>(bulk, s, in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, st);
 
 static int segment_gather_sum(const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *off,
                               const uint32_t *slot_of, uint32_t base, uint32_t n_rows, uint64_t n_edges, uint32_t F,
@@ -377,16 +412,16 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
     return 0;
   NTS_ARG_CHECK(in && out && idx && off, "null pointer passed to segment_gather_sum");
   NTS_ARG_CHECK(n_edges < 0xffffffffull, "chunk edge count must fit uint32 offsets");
-  LaunchShape s = pick_shape(in, out, F);
+  LaunchShape s = pick_shape(in, out, F, 0);
   // edges per warp: multiple of 32; shrink for small inputs so the grid still fills 148 SMs
-  uint32_t Q = g_edges_per_warp > 0 ? (uint32_t)g_edges_per_warp : 256u;
+  uint32_t Q = g_edges_per_warp > 0 ? (uint32_t)g_edges_per_warp : 512u;
   if (g_edges_per_warp <= 0) {
     const uint64_t want_warps = (uint64_t)sm_count() * 64;
     while (Q > 32 && ((n_edges + Q - 1) / Q) * s.tiles < want_warps)
       Q >>= 1;
   }
   Q = (Q + 31u) & ~31u;
-  int variant = g_variant == 0 ? 2 : g_variant; // measured on B200: bulk-staged indices are ~20% faster
+  int variant = g_variant == 0 ? 2 : g_variant; // measured on B200: bulk-staged indices are ~15-20% faster
   bool bulk = variant == 2;
   // the bulk copies need 16-byte aligned index/weight arrays (cudaMalloc gives 256)
   if (bulk && !(aligned_to(idx, 16) && (!w || aligned_to(w, 16)))) {
@@ -394,41 +429,42 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
     variant = 1;
   }
   g_last_variant = variant;
-  // experiment hook: NTS_AGG_TUNE="U,MINB" picks another (U, occupancy) point for the two headline shapes
-  if (const char *tune = getenv("NTS_AGG_TUNE")) {
-    int tu = 0, tb = 0;
-    if (sscanf(tune, "%d,%d", &tu, &tb) == 2) {
-#define NTS_TUNE_CASE(V_, K_, U_, B_)                                                                        \
-  if (s.vec == V_ && s.k == K_ && tu == U_ && tb == B_)                                                       \
-    return launch_shape<V_, K_, U_, B_>(bulk, in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, s.tiles, st);
-      NTS_TUNE_CASE(2, 5, 2, 4)
-      NTS_TUNE_CASE(2, 5, 2, 3)
-      NTS_TUNE_CASE(2, 5, 4, 3)
-      NTS_TUNE_CASE(2, 5, 8, 1)
-      NTS_TUNE_CASE(2, 5, 1, 4)
-      NTS_TUNE_CASE(4, 1, 8, 4)
-      NTS_TUNE_CASE(4, 1, 4, 6)
-      NTS_TUNE_CASE(4, 1, 8, 6)
-      NTS_TUNE_CASE(4, 1, 16, 2)
-      NTS_TUNE_CASE(4, 1, 16, 3)
-#undef NTS_TUNE_CASE
-    }
-  }
-  NTS_SHAPE_CASE(4, 1, 8)
-  NTS_SHAPE_CASE(4, 2, 4)
-  NTS_SHAPE_CASE(4, 3, 2)
-  NTS_SHAPE_CASE(4, 4, 2)
-  NTS_SHAPE_CASE(2, 1, 8)
-  NTS_SHAPE_CASE(2, 2, 8)
-  NTS_SHAPE_CASE(2, 3, 4)
-  NTS_SHAPE_CASE(2, 4, 4)
-  NTS_SHAPE_CASE(2, 5, 4)
-  NTS_SHAPE_CASE(1, 1, 8)
-  NTS_SHAPE_CASE(1, 2, 8)
-  NTS_SHAPE_CASE(1, 3, 8)
-  NTS_SHAPE_CASE(1, 4, 8)
-  NTS_SHAPE_CASE(1, 5, 8)
-  return fail(-1, "no kernel instantiation for this feature width", __FILE__, __LINE__);
+  // default (U, MINB) points
+  NTS_CASE(4, 1, 8, 3)
+  NTS_CASE(4, 2, 4, 1)
+  NTS_CASE(4, 3, 2, 1)
+  NTS_CASE(4, 4, 2, 1)
+  NTS_CASE(2, 1, 8, 1)
+  NTS_CASE(2, 2, 8, 1)
+  NTS_CASE(2, 3, 4, 1)
+  NTS_CASE(2, 4, 4, 1)
+  NTS_CASE(2, 5, 2, 3)
+  NTS_CASE(1, 1, 8, 1)
+  NTS_CASE(1, 2, 8, 1)
+  NTS_CASE(1, 3, 8, 1)
+  NTS_CASE(1, 4, 8, 1)
+  NTS_CASE(1, 5, 8, 1)
+  // extra points reachable through NTS_AGG_TUNE / NTS_AGG_TILES (tuning sweeps, tools/tune_aggregate.py)
+  NTS_CASE(4, 1, 8, 1)
+  NTS_CASE(4, 1, 8, 4)
+  NTS_CASE(4, 1, 16, 2)
+  NTS_CASE(4, 1, 4, 4)
+  NTS_CASE(2, 5, 4, 1)
+  NTS_CASE(2, 5, 2, 2)
+  NTS_CASE(2, 5, 4, 2)
+  NTS_CASE(2, 4, 2, 3)
+  NTS_CASE(2, 4, 4, 2)
+  NTS_CASE(2, 3, 2, 3)
+  NTS_CASE(2, 3, 4, 3)
+  NTS_CASE(2, 3, 4, 2)
+  NTS_CASE(2, 2, 4, 3)
+  NTS_CASE(2, 2, 4, 4)
+  NTS_CASE(2, 2, 8, 2)
+  NTS_CASE(2, 2, 8, 3)
+  NTS_CASE(2, 1, 8, 4)
+  NTS_CASE(2, 1, 8, 3)
+  NTS_CASE(2, 1, 16, 2)
+  return fail(-1, "no kernel instantiation for this (vector width, chunks, U, occupancy) point", __FILE__, __LINE__);
 }
 
 } // namespace nts
