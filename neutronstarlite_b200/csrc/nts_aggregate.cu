@@ -353,12 +353,12 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uin
   s.minb = 1;
   int budget = 40 / (s.k * s.vec);
   s.u = budget >= 8 ? 8 : (budget >= 4 ? 4 : 2);
-  if (s.vec == 2 && s.k == 5) {
+  if (s.vec == 2 && s.k == 5) { // F=602: 15.5 ms vs 16.4 (U=4) / 16.1 (U=2, 3 CTAs) on the Reddit-shaped graph
     s.u = 2;
-    s.minb = 3;
-  } else if (s.vec == 4 && s.k == 1) {
-    s.u = 8;
-    s.minb = 3;
+    s.minb = 2;
+  } else if (s.vec == 4 && s.k == 1) { // F=128: 3.48 ms vs 3.76 (U=8, 3 CTAs) / 4.65 (U=8, unconstrained)
+    s.u = 4;
+    s.minb = 4;
   }
   if (const char *tune = getenv("NTS_AGG_TUNE")) {
     int tu = 0, tb = 0;
@@ -430,7 +430,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   }
   g_last_variant = variant;
   // default (U, MINB) points
-  NTS_CASE(4, 1, 8, 3)
+  NTS_CASE(4, 1, 4, 4)
   NTS_CASE(4, 2, 4, 1)
   NTS_CASE(4, 3, 2, 1)
   NTS_CASE(4, 4, 2, 1)
@@ -438,7 +438,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   NTS_CASE(2, 2, 8, 1)
   NTS_CASE(2, 3, 4, 1)
   NTS_CASE(2, 4, 4, 1)
-  NTS_CASE(2, 5, 2, 3)
+  NTS_CASE(2, 5, 2, 2)
   NTS_CASE(1, 1, 8, 1)
   NTS_CASE(1, 2, 8, 1)
   NTS_CASE(1, 3, 8, 1)
@@ -448,9 +448,9 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   NTS_CASE(4, 1, 8, 1)
   NTS_CASE(4, 1, 8, 4)
   NTS_CASE(4, 1, 16, 2)
-  NTS_CASE(4, 1, 4, 4)
+  NTS_CASE(4, 1, 8, 3)
   NTS_CASE(2, 5, 4, 1)
-  NTS_CASE(2, 5, 2, 2)
+  NTS_CASE(2, 5, 2, 3)
   NTS_CASE(2, 5, 4, 2)
   NTS_CASE(2, 4, 2, 3)
   NTS_CASE(2, 4, 4, 2)
