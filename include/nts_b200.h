@@ -103,6 +103,15 @@ int nts_segment_gather_sum_slots(const float *input, float *output, const float 
                                  const nts_vid_t *slot_of, nts_vid_t n_rows, uint64_t n_edges,
                                  nts_vid_t feature_size, void *stream);
 
+/* Multi-head fused GAT aggregation: weight is [n_edges, heads] row-major, feature_size = heads * D and head h scales
+ * columns [h*D, (h+1)*D):  output[r, hD+c] += sum_e weight[e,h] * input[row(e), hD+c],  row(e) = slot_of ?
+ * slot_of[indices[e]] : indices[e] - index_base.  heads = 1 is the single-head operator above.  (The reference's
+ * DistAggregateDstFuseWeight has one head; 8 heads is config D of BASELINE.json.) */
+int nts_segment_gather_sum_heads(const float *input, float *output, const float *weight,
+                                 const nts_vid_t *indices, const nts_vid_t *offsets, const nts_vid_t *slot_of,
+                                 nts_vid_t index_base, nts_vid_t n_rows, uint64_t n_edges,
+                                 nts_vid_t feature_size, nts_vid_t heads, void *stream);
+
 /* Tuning / introspection of the aggregation kernel (does not change results beyond fp32
  * re-association): variant 0 = auto, see DESIGN.md "kernel variants". */
 int nts_aggregate_set_variant(int variant, int edges_per_warp);
@@ -156,6 +165,13 @@ int nts_aggregate_dst_fuse_weight_backward(float *mirror_grad, float *edge_weigh
                                            const nts_vid_t *column_offset,
                                            const nts_vid_t *mirror_index, nts_vid_t batch_size,
                                            nts_vid_t feature_size, void *stream);
+/* multi-head form: edge_weight / edge_weight_grad are [E, heads], head h owns columns [h*D, (h+1)*D) */
+int nts_aggregate_dst_fuse_weight_backward_heads(float *mirror_grad, float *edge_weight_grad,
+                                                 const float *mirror, const float *edge_weight,
+                                                 const float *dst_grad, const nts_vid_t *row_indices,
+                                                 const nts_vid_t *column_offset,
+                                                 const nts_vid_t *mirror_index, nts_vid_t batch_size,
+                                                 nts_vid_t feature_size, nts_vid_t heads, void *stream);
 
 /* ---- (vid,row) message records: the reference's host-staged exchange format (comm/network.h:143-149) ---
  * record k = { uint32 vid; float row[feature_size]; }, read through mapped pinned host memory. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "nts_gather_by_dst_from_src": (_int, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _int, _vp]),
     "nts_gather_by_src_from_dst": (_int, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _int, _vp]),
     "nts_segment_gather_sum_slots": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u64, _u32, _vp]),
+    "nts_segment_gather_sum_heads": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u64, _u32, _u32, _vp]),
     "nts_aggregate_set_variant": (_int, [_int, _int]),
     "nts_aggregate_last_launch": (_int, [C.POINTER(_int)] * 4),
     "nts_kernel_launch_count": (_u64, []),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "nts_edge_softmax_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "nts_scatter_grad_back_to_message": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _vp]),
     "nts_aggregate_dst_fuse_weight_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "nts_aggregate_dst_fuse_weight_backward_heads": (_int, [_vp] * 8 + [_u32, _u32, _u32, _vp]),
     "nts_deserialize_records": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp]),
     "nts_aggregate_records": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp]),
     "nts_gather_rows": (_int, [_vp, _vp, _vp, _u32, _u32, _vp]),

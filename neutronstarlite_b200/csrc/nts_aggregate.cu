@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
                               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
                               const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
                               uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
-                              uint32_t tile_major) {
+                              uint32_t tile_major, uint32_t w_stride) {
   using V = typename Vec<VEC>::type;
   const uint32_t n_edges = (uint32_t)n_edges64;
   const uint32_t lane = threadIdx.x & 31;
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
       if (lane < cnt) {
         uint32_t id = __ldg(idx + e + lane);
         my_src = slot_of ? __ldg(slot_of + id) : id - base;
-        if (w)
-          my_w = __ldg(w + e + lane);
+        if (w) // multi-head weights [E, H]: column tile t is head t (w_stride = H), else one weight per edge
+          my_w = __ldg(w + (size_t)(e + lane) * w_stride + (w_stride > 1 ? tile : 0u));
       }
     }
     uint32_t j = 0;
@@ -319,11 +319,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 // ---- host-side dispatch ---------------------------------------------------------------------------------
 struct LaunchShape {
   int vec, k, u, minb;
-  uint32_t tiles, tile_vecs, tile_major;
+  uint32_t tiles, tile_vecs, tile_major, w_stride;
 };
 
-static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uint32_t n_src_rows_hint) {
+static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uint32_t heads) {
   LaunchShape s;
+  s.w_stride = 1;
   bool a16 = aligned_to(in, 16) && aligned_to(out, 16);
   bool a8 = aligned_to(in, 8) && aligned_to(out, 8);
   if (F % 4 == 0 && a16)
@@ -337,7 +338,6 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uin
   const uint32_t kmax = (s.vec == 4) ? 4 : 5;
   s.tiles = (chunks + kmax - 1) / kmax;
   s.tile_major = 0;
-  (void)n_src_rows_hint;
   // experiment / tuning hook: NTS_AGG_TILES="tiles,tile_major"
   if (const char *e = getenv("NTS_AGG_TILES")) {
     int t = 0, m = 0;
@@ -347,8 +347,15 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uin
     }
   }
   s.tile_vecs = (nvec + s.tiles - 1) / s.tiles;
+  if (heads > 1) { // one column tile per attention head: tile t covers columns [t*D, (t+1)*D)
+    s.tiles = heads;
+    s.tile_major = 0;
+    s.tile_vecs = nvec / heads;
+    s.w_stride = heads;
+  }
   s.k = (int)((s.tile_vecs + 31) / 32);
-  s.tiles = (nvec + s.tile_vecs - 1) / s.tile_vecs;
+  if (heads <= 1)
+    s.tiles = (nvec + s.tile_vecs - 1) / s.tile_vecs;
   // (U, min CTAs/SM): measured on B200 for the headline shapes (profiles/tune_r1_*.jsonl), generic rule otherwise
   s.minb = 1;
   int budget = 40 / (s.k * s.vec);
@@ -391,11 +398,12 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
     NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_last_smem = (int)smem;
     kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F,
-                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major);
+                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major, sh.w_stride);
   } else {
     g_last_smem = 0;
     segment_gather_sum_kernel<VEC, K, U, false, MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-        in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major);
+        in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
+        sh.w_stride);
   }
   NTS_LAUNCH_CHECK();
   return 0;
@@ -407,12 +415,28 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
 
 static int segment_gather_sum(const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *off,
                               const uint32_t *slot_of, uint32_t base, uint32_t n_rows, uint64_t n_edges, uint32_t F,
-                              cudaStream_t st) {
+                              cudaStream_t st, uint32_t heads = 1) {
   if (n_rows == 0 || n_edges == 0 || F == 0)
     return 0;
   NTS_ARG_CHECK(in && out && idx && off, "null pointer passed to segment_gather_sum");
   NTS_ARG_CHECK(n_edges < 0xffffffffull, "chunk edge count must fit uint32 offsets");
-  LaunchShape s = pick_shape(in, out, F, 0);
+  if (heads > 1) {
+    NTS_ARG_CHECK(w != nullptr, "multi-head aggregation needs the [E, heads] weight matrix");
+    NTS_ARG_CHECK(F % heads == 0, "feature_size must be a multiple of heads");
+  }
+  LaunchShape s = pick_shape(in, out, F, heads);
+  if (heads > 1) {
+    // the head width must be a whole number of vectors; fall back to narrower vectors if it is not
+    while (s.vec > 1 && (F / heads) % s.vec != 0) {
+      s.vec >>= 1;
+      s.tile_vecs = (F / s.vec) / heads;
+      s.k = (int)((s.tile_vecs + 31) / 32);
+    }
+    NTS_ARG_CHECK(s.k >= 1 && s.k <= 5, "head width too large for one column tile");
+    s.minb = 1;
+    int budget = 40 / (s.k * s.vec);
+    s.u = budget >= 8 ? 8 : (budget >= 4 ? 4 : 2);
+  }
   // edges per warp: multiple of 32; shrink for small inputs so the grid still fills 148 SMs
   uint32_t Q = g_edges_per_warp > 0 ? (uint32_t)g_edges_per_warp : 512u;
   if (g_edges_per_warp <= 0) {
@@ -422,7 +446,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   }
   Q = (Q + 31u) & ~31u;
   int variant = g_variant == 0 ? 2 : g_variant; // measured on B200: bulk-staged indices are ~15-20% faster
-  bool bulk = variant == 2;
+  bool bulk = variant == 2 && heads <= 1; // [E, H] weights are read per lane + shuffled, not bulk-staged
   // the bulk copies need 16-byte aligned index/weight arrays (cudaMalloc gives 256)
   if (bulk && !(aligned_to(idx, 16) && (!w || aligned_to(w, 16)))) {
     bulk = false;
@@ -484,6 +508,15 @@ int nts_segment_gather_sum_slots(const float *input, float *output, const float 
   NTS_ARG_CHECK(slot_of != nullptr, "slot table is null");
   return nts::segment_gather_sum(input, output, weight, indices, offsets, slot_of, 0, n_rows, n_edges, feature_size,
                                  nts::as_stream(stream));
+}
+
+int nts_segment_gather_sum_heads(const float *input, float *output, const float *weight, const nts_vid_t *indices,
+                                 const nts_vid_t *offsets, const nts_vid_t *slot_of, nts_vid_t index_base,
+                                 nts_vid_t n_rows, uint64_t n_edges, nts_vid_t feature_size, nts_vid_t heads,
+                                 void *stream) {
+  NTS_ARG_CHECK(heads >= 1, "heads must be >= 1");
+  return nts::segment_gather_sum(input, output, weight, indices, offsets, slot_of, index_base, n_rows, n_edges,
+                                 feature_size, nts::as_stream(stream), heads);
 }
 
 int nts_gather_by_dst_from_src(const float *input, float *output, const float *weight_forward,

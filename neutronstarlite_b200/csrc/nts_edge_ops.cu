@@ -269,37 +269,39 @@ __global__ void __launch_bounds__(kThreads)
                                 const float *__restrict__ mirror, const float *__restrict__ a,
                                 const float *__restrict__ g, const uint32_t *__restrict__ row_idx,
                                 const uint32_t *__restrict__ off, const uint32_t *__restrict__ mirror_index,
-                                uint32_t n_rows, uint32_t F) {
+                                uint32_t n_rows, uint32_t F, uint32_t heads) {
   using V = typename Vec<VEC>::type;
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t nvec = F / VEC;
+  const uint32_t head_vecs = F / VEC / heads; // vectors per head (host guarantees divisibility)
   const uint32_t n_edges = __ldg(off + n_rows); // E_p stays on the device: no host read-back
   const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
   for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kEdgeQuantum < n_edges; qw += nwarps) {
-  const uint32_t e0 = (uint32_t)(qw * kEdgeQuantum);
-  const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kEdgeQuantum);
-  uint32_t row = eo_find_row(off, n_rows, e0);
-  uint32_t row_end = __ldg(off + row + 1);
-  for (uint32_t e = e0; e < e1; e++) {
-    while (e >= row_end) {
-      row++;
-      row_end = __ldg(off + row + 1);
+    const uint32_t e0 = (uint32_t)(qw * kEdgeQuantum);
+    const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kEdgeQuantum);
+    uint32_t row = eo_find_row(off, n_rows, e0);
+    uint32_t row_end = __ldg(off + row + 1);
+    for (uint32_t e = e0; e < e1; e++) {
+      while (e >= row_end) {
+        row++;
+        row_end = __ldg(off + row + 1);
+      }
+      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
+      const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F);
+      const V *mm = reinterpret_cast<const V *>(mirror + (size_t)slot * F);
+      V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F);
+      for (uint32_t h = 0; h < heads; h++) {
+        const float ae = __ldg(a + (size_t)e * heads + h);
+        float dot = 0.f;
+        for (uint32_t c = h * head_vecs + lane; c < (h + 1) * head_vecs; c += 32) {
+          V gv = __ldg(gm + c);
+          dot += vec_dot(__ldg(mm + c), gv);
+          vec_red_add<VEC>(dm + c, vec_scale(gv, ae));
+        }
+        dot = warp_sum(dot);
+        if (lane == 0)
+          a_grad[(size_t)e * heads + h] = dot;
+      }
     }
-    const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
-    const float ae = __ldg(a + e);
-    const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F);
-    const V *mm = reinterpret_cast<const V *>(mirror + (size_t)slot * F);
-    V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F);
-    float dot = 0.f;
-    for (uint32_t c = lane; c < nvec; c += 32) {
-      V gv = __ldg(gm + c);
-      dot += vec_dot(__ldg(mm + c), gv);
-      vec_red_add<VEC>(dm + c, vec_scale(gv, ae));
-    }
-    dot = warp_sum(dot);
-    if (lane == 0)
-      a_grad[e] = dot;
-  }
   } // quantum loop
 }
 
@@ -495,33 +497,46 @@ int nts_edge_softmax_backward(float *msg_input_grad, const float *msg_output_gra
   return 0;
 }
 
-int nts_aggregate_dst_fuse_weight_backward(float *mirror_grad, float *edge_weight_grad, const float *mirror,
-                                           const float *edge_weight, const float *dst_grad,
-                                           const nts_vid_t *row_indices, const nts_vid_t *column_offset,
-                                           const nts_vid_t *mirror_index, nts_vid_t batch_size,
-                                           nts_vid_t feature_size, void *stream) {
+int nts_aggregate_dst_fuse_weight_backward_heads(float *mirror_grad, float *edge_weight_grad, const float *mirror,
+                                                 const float *edge_weight, const float *dst_grad,
+                                                 const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                                 const nts_vid_t *mirror_index, nts_vid_t batch_size,
+                                                 nts_vid_t feature_size, nts_vid_t heads, void *stream) {
   cudaStream_t st = as_stream(stream);
   if (batch_size == 0 || feature_size == 0)
     return 0;
   NTS_ARG_CHECK(mirror_grad && edge_weight_grad && mirror && edge_weight && dst_grad && row_indices &&
                     column_offset && mirror_index,
                 "null pointer passed to fuse-weight backward");
+  NTS_ARG_CHECK(heads >= 1 && feature_size % heads == 0, "feature_size must be a multiple of heads");
   int vec = pick_vec(feature_size, mirror_grad, mirror, dst_grad);
+  while (vec > 1 && (feature_size / heads) % vec != 0)
+    vec >>= 1;
   unsigned grid = full_grid();
   if (vec == 4)
     fuse_weight_backward_kernel<4><<<grid, kThreads, 0, st>>>(mirror_grad, edge_weight_grad, mirror, edge_weight,
                                                               dst_grad, row_indices, column_offset, mirror_index,
-                                                              batch_size, feature_size);
+                                                              batch_size, feature_size, heads);
   else if (vec == 2)
     fuse_weight_backward_kernel<2><<<grid, kThreads, 0, st>>>(mirror_grad, edge_weight_grad, mirror, edge_weight,
                                                               dst_grad, row_indices, column_offset, mirror_index,
-                                                              batch_size, feature_size);
+                                                              batch_size, feature_size, heads);
   else
     fuse_weight_backward_kernel<1><<<grid, kThreads, 0, st>>>(mirror_grad, edge_weight_grad, mirror, edge_weight,
                                                               dst_grad, row_indices, column_offset, mirror_index,
-                                                              batch_size, feature_size);
+                                                              batch_size, feature_size, heads);
   NTS_LAUNCH_CHECK();
   return 0;
+}
+
+int nts_aggregate_dst_fuse_weight_backward(float *mirror_grad, float *edge_weight_grad, const float *mirror,
+                                           const float *edge_weight, const float *dst_grad,
+                                           const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                           const nts_vid_t *mirror_index, nts_vid_t batch_size,
+                                           nts_vid_t feature_size, void *stream) {
+  return nts_aggregate_dst_fuse_weight_backward_heads(mirror_grad, edge_weight_grad, mirror, edge_weight, dst_grad,
+                                                      row_indices, column_offset, mirror_index, batch_size,
+                                                      feature_size, 1, stream);
 }
 
 int nts_deserialize_records(float *mirror, const float *records, nts_vid_t n_records, nts_vid_t feature_size,

@@ -264,10 +264,11 @@ class DistGPUAggregateDstFuseWeight(_EdgeOp):
         x = _check_input(f_input)
         a = _check_input(e_weight, "edge weight")
         self._mirror, self._a = x, a
+        heads = int(a.shape[1])  # [E, H]: head h weights columns [h*D, (h+1)*D); H = 1 is the reference's operator
         out = torch.zeros((pg.owned_vertices, x.shape[1]), dtype=torch.float32, device=x.device)
-        _lib.call("nts_segment_gather_sum_slots", _ptr(x), _ptr(out), _ptr(a), _ptr(pg.row_indices_gpu),
-                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, pg.owned_edges,
-                  x.shape[1], _stream())
+        _lib.call("nts_segment_gather_sum_heads", _ptr(x), _ptr(out), _ptr(a), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), 0, pg.owned_vertices, pg.owned_edges,
+                  x.shape[1], heads, _stream())
         return out
 
     def backward(self, f_output_grad):
@@ -275,9 +276,9 @@ class DistGPUAggregateDstFuseWeight(_EdgeOp):
         g = _check_input(f_output_grad, "output_grad")
         dm = torch.zeros((pg.owned_mirrors, g.shape[1]), dtype=torch.float32, device=g.device)
         self.e_weight_grad = torch.zeros_like(self._a)
-        _lib.call("nts_aggregate_dst_fuse_weight_backward", _ptr(dm), _ptr(self.e_weight_grad), _ptr(self._mirror),
-                  _ptr(self._a), _ptr(g), _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu),
-                  _ptr(pg.mirror_index_gpu), pg.owned_vertices, g.shape[1], _stream())
+        _lib.call("nts_aggregate_dst_fuse_weight_backward_heads", _ptr(dm), _ptr(self.e_weight_grad),
+                  _ptr(self._mirror), _ptr(self._a), _ptr(g), _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu),
+                  _ptr(pg.mirror_index_gpu), pg.owned_vertices, g.shape[1], int(self._a.shape[1]), _stream())
         return dm
 
     def get_additional_grad(self):

@@ -350,3 +350,45 @@ def test_properties_at_scale():
     for name in ("edge_weight_forward", "edge_weight_backward"):
         assert np.array_equal(getattr(hc, name).view(np.uint32),
                               getattr(dc, name + "_gpu").cpu().numpy().view(np.uint32)), name
+
+
+@pytest.mark.parametrize("H,D", [(1, 24), (2, 16), (8, 64), (8, 8), (3, 5)])
+def test_multi_head_fused_aggregation(H, D):
+    """Fused GAT aggregation with [E, H] attention weights (config D of BASELINE.json uses 8 heads): head h scales
+    columns [h*D, (h+1)*D).  Oracle: the single-head C loop applied per head; backward against the numpy restatement
+    of DistAggregateDstFuseWeight::backward (core/ntsDistCPUGraphOp.hpp:548-589, without its extra add)."""
+    from neutronstarlite_b200 import ops
+    from neutronstarlite_b200.graph import PartitionedGraph
+    rng = np.random.default_rng(H * 100 + D)
+    Vp, Vg, E = 600, 2000, 20000
+    off, idx, _ = random_csr(Vp, Vg, E, seed=H + D)
+    used = np.unique(idx)
+    mi = np.zeros(Vg + 1, dtype=np.uint32)
+    mi[used + 1] = 1
+    mi = np.cumsum(mi, dtype=np.uint32)
+    M = int(mi[-1])
+    F = H * D
+    mirror = rng.uniform(-1, 1, (M, F)).astype(np.float32)
+    a = rng.uniform(0, 1, (E, H)).astype(np.float32)
+    g = rng.uniform(-1, 1, (Vp, F)).astype(np.float32)
+    pg = PartitionedGraph(None, 1, 0, np.array([0, Vp], dtype=np.uint32))
+    pg.owned_vertices, pg.owned_edges, pg.owned_mirrors = Vp, E, M
+    pg.column_offset_gpu, pg.row_indices_gpu, pg.mirror_index_gpu = up_u32(off), up_u32(idx), up_u32(mi)
+    op = ops.DistGPUAggregateDstFuseWeight(pg)
+    y = op.forward(up(mirror), up(a)).cpu().numpy()
+    slot = mi[idx]
+    ref = np.zeros((Vp, F), dtype=np.float32)
+    for h in range(H):
+        ref[:, h * D:(h + 1) * D] = oracle_c.segment_gather_sum(off, slot, a[:, h], mirror[:, h * D:(h + 1) * D])
+    close(y, ref)
+    dm = op.backward(up(g)).cpu().numpy()
+    dw = op.get_additional_grad().cpu().numpy()
+    dm_ref = np.zeros((M, F), dtype=np.float32)
+    dw_ref = np.zeros((E, H), dtype=np.float32)
+    for h in range(H):
+        sl = slice(h * D, (h + 1) * D)
+        dmh, dwh = O.aggregate_dst_fuse_weight_backward(off, idx, mi, mirror[:, sl], a[:, h:h + 1], g[:, sl], M)
+        dm_ref[:, sl] = dmh
+        dw_ref[:, h:h + 1] = dwh
+    close(dm, dm_ref)
+    close(dw, dw_ref)
