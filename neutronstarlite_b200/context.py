@@ -25,9 +25,15 @@ class _Entry:
 
 
 class NtsContext:
-    def __init__(self):
+    def __init__(self, sum_fanout_grads=False):
         self.tape = []
         self.training = True
+        # The reference overwrites: when a graph-op output feeds BOTH another graph op (gradient assigned through the
+        # tape) and an NN segment (gradient accumulated in tensor.grad by torch), only the assigned one survives
+        # (`if (output_grad[top].dim() < 2) output_grad[top] = output.top().grad()`, ntsContext.hpp:289-291) - e.g. the
+        # attention-score path mirror -> src_att of GAT_CPU_DIST_OPTM.hpp is dropped.  sum_fanout_grads=True adds the
+        # two contributions instead (the mathematically complete gradient); default is the reference behaviour.
+        self.sum_fanout_grads = sum_fanout_grads
 
     @property
     def count(self):
@@ -97,6 +103,8 @@ class NtsContext:
             idx = len(self.tape) - 1
             if e.grad is None or e.grad.dim() < 2:
                 e.grad = e.output.grad
+            elif self.sum_fanout_grads and e.kind != NNOP and e.output.grad is not None:
+                e.grad = e.grad + e.output.grad
             if e.kind in (GRAPHOP, BIGRAPHOP):
                 g_in = e.op.backward(e.grad)
                 k = self._producer_of(e.i_id1, idx)

@@ -179,6 +179,60 @@ class GpuExchange:
         if ev:
             ev[1].record()
 
+    # ---- mirror fetch / return (DistGPUGetDepNbrOp, core/ntsDistGPUGraphOp.hpp:48-143) ----------------------------
+    def fetch_mirrors(self, x):
+        """mirror[MirrorIndex[s], :] = X[s, :] for every source s of a local in-edge, [owned_mirrors, F].
+        MirrorIndex numbers active sources in global-id order = partition order, so the mirror matrix is the
+        concatenation over partitions i of the needed rows of partition i: exactly the output layout of one
+        all-to-all(v) whose self segment carries this rank's own active rows.  (The reference moves the whole
+        feature matrix to the host, through MPI and back, core/ntsDistGPUGraphOp.hpp:56-98.)"""
+        plan, P, p = self.plan, self.P, self.p
+        F = x.shape[1]
+        cur = torch.cuda.current_stream()
+        M = sum(plan.need_count)
+        mirror = torch.zeros((M, F), dtype=torch.float32, device=x.device)
+        if P == 1:
+            if M:
+                _lib.call("nts_gather_rows", _ptr(mirror), _ptr(x), _ptr(plan.need[0]), M, F, cur.cuda_stream)
+            return mirror
+        rows_out = [plan.send_rows[j] if j != p else plan.need[p] for j in range(P)]
+        n_out = [int(r.numel()) for r in rows_out]
+        send = self._buf("msend", sum(n_out), F)
+        pos = 0
+        for j in range(P):
+            if n_out[j]:
+                _lib.call("nts_gather_rows", _ptr(send[pos:pos + n_out[j]]), _ptr(x), _ptr(rows_out[j]), n_out[j], F,
+                          cur.cuda_stream)
+            pos += n_out[j]
+        dist.all_to_all_single(mirror, send, output_split_sizes=list(plan.need_count), input_split_sizes=n_out,
+                               group=self.group)
+        return mirror
+
+    def return_mirror_grads(self, gm):
+        """DistGPUGetDepNbrOp::backward: every mirror gradient goes back to the owner of the source vertex, who sums
+        what arrives from all partitions (one unique-row scatter-add per sender)."""
+        pg, plan, P, p = self.pg, self.plan, self.P, self.p
+        F = gm.shape[1]
+        cur = torch.cuda.current_stream()
+        dx = torch.zeros((pg.owned_vertices, F), dtype=torch.float32, device=gm.device)
+        if P == 1:
+            if gm.shape[0]:
+                _lib.call("nts_scatter_add_rows", _ptr(dx), _ptr(gm), _ptr(plan.need[0]), gm.shape[0], F,
+                          cur.cuda_stream)
+            return dx
+        rows_in = [plan.send_rows[j] if j != p else plan.need[p] for j in range(P)]
+        n_in = [int(r.numel()) for r in rows_in]
+        recv = self._buf("mrecv", sum(n_in), F)
+        dist.all_to_all_single(recv, gm.contiguous(), output_split_sizes=n_in,
+                               input_split_sizes=list(plan.need_count), group=self.group)
+        pos = 0
+        for j in range(P):
+            if n_in[j]:
+                _lib.call("nts_scatter_add_rows", _ptr(dx), _ptr(recv[pos:pos + n_in[j]]), _ptr(rows_in[j]), n_in[j],
+                          F, cur.cuda_stream)
+            pos += n_in[j]
+        return dx
+
     # ---- backward ----------------------------------------------------------------------------------------------
     def backward(self, g):
         pg, plan, P, p = self.pg, self.plan, self.P, self.p

@@ -162,6 +162,25 @@ class _EdgeOp(ntsGraphOp):
         return pg
 
 
+class DistGPUGetDepNbrOp(ntsGraphOp):
+    """core/ntsDistGPUGraphOp.hpp:48-143: fetch the feature rows of every (local or remote) source of a local
+    in-edge into the mirror matrix [owned_mirrors, F]; backward returns mirror gradients to the owners.
+    Device-resident here (f4 of SURVEY 8f): no .cpu()/MPI/.cuda() round trip."""
+
+    def __init__(self, partitioned_graph, active=None, exchange=None):
+        super().__init__(partitioned_graph, active)
+        if exchange is None:
+            from .exchange import default_exchange
+            exchange = default_exchange(partitioned_graph)
+        self.exchange = exchange
+
+    def forward(self, f_input, f_input1=None):
+        return self.exchange.fetch_mirrors(_check_input(f_input))
+
+    def backward(self, f_output_grad):
+        return self.exchange.return_mirror_grads(_check_input(f_output_grad, "output_grad"))
+
+
 class DistGPUScatterSrc(_EdgeOp):
     """core/ntsDistGPUGraphOp.hpp:100-176: mirror [M,F] -> edge messages [E_p,F]."""
 

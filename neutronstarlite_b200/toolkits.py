@@ -158,3 +158,93 @@ class GCNImpl:
         self.Update()
         self.epoch += 1
         return self.loss, acc
+
+
+class GATImpl:
+    """Multi-head GAT on the fused aggregation path - the flow of toolkits/GAT_CPU_DIST_OPTM.hpp:196-241 (per-vertex
+    attention scores -> [E, H] edge logits -> edge softmax -> DistAggregateDstFuseWeight) on the GPU operators, with
+    H heads (the reference has one).  `layers` are total widths, e.g. [602, 64, 64, 41] with heads=8 gives hidden
+    layers of 8 heads x 8 and a single-head output layer (config D of BASELINE.json).  Never materialises an [E, F]
+    message; the only edge-sized tensors are [E, H]."""
+
+    def __init__(self, partitioned_graph, layers, features, labels, mask, heads=8, learn_rate=0.01,
+                 weight_decay=0.0001, exchange=None, seed=0, sum_fanout_grads=True):
+        self.pg = partitioned_graph
+        self.layers = list(layers)
+        self.device = features.device
+        self.heads = [heads] * (len(self.layers) - 2) + [1]
+        self.ctx = NtsContext(sum_fanout_grads=sum_fanout_grads)
+        gen = torch.Generator().manual_seed(seed)
+        self.P, self.al, self.ar = [], [], []
+        for i in range(len(self.layers) - 1):
+            H = self.heads[i]
+            D = self.layers[i + 1] // H
+            assert H * D == self.layers[i + 1], "layer width must be a multiple of heads"
+            mk = lambda a, b: Parameter(a, b, learn_rate, 0.9, 0.999, 1e-9, weight_decay, device=self.device,
+                                        generator=gen)
+            for lst, shape in ((self.P, (self.layers[i], H * D)), (self.al, (H, D)), (self.ar, (H, D))):
+                prm = mk(*shape)
+                prm.init_parameter()
+                lst.append(prm)
+        if exchange is None:
+            from .exchange import GpuExchange
+            exchange = GpuExchange(partitioned_graph)
+        self.exchange = exchange
+        self.L_GT = labels.to(self.device)
+        self.MASK = mask.to(self.device)
+        self.train_rows = (self.MASK == 0).nonzero().view(-1)
+        self.X = [None] * len(self.layers)
+        self.X[0] = features.requires_grad_(True)
+        self.loss = None
+        self.epoch = 0
+
+    def params(self):
+        return self.P + self.al + self.ar
+
+    def Forward(self):
+        ctx, pg = self.ctx, self.pg
+        for i in range(len(self.layers) - 1):
+            H = self.heads[i]
+            D = self.layers[i + 1] // H
+            last = i == len(self.layers) - 2
+            X_trans = ctx.runVertexForward(lambda x, _i=i: self.P[_i].forward(x), self.X[i])
+            mirror = ctx.runGraphOp(ops.DistGPUGetDepNbrOp, pg, None, X_trans.contiguous(), exchange=self.exchange)
+            src_att = ctx.runVertexForward(
+                lambda m, _i=i: (m.view(-1, H, D) * self.al[_i].W).sum(-1).contiguous(), mirror)
+            dst_att = ctx.runVertexForward(
+                lambda x, _i=i: (x.view(-1, H, D) * self.ar[_i].W).sum(-1).contiguous(), X_trans)
+            e_src = ctx.runGraphOp(ops.DistGPUScatterSrc, pg, None, src_att)
+            e_dst = ctx.runGraphOp(ops.DistGPUScatterDst, pg, None, dst_att)
+            e_msg = e_src + e_dst  # (the reference concatenates the two [E,1] columns and sums them, :218-224)
+            m = ctx.runEdgeForward(lambda t: torch.nn.functional.leaky_relu(t, 0.2), e_msg)
+            a = ctx.runGraphOp(ops.DistGPUEdgeSoftMax, pg, None, m)
+            nbr = ctx.runGraphOp(ops.DistGPUAggregateDstFuseWeight, pg, None, mirror, a)
+            if last:
+                self.X[i + 1] = ctx.runVertexForward(lambda t: t.log_softmax(1), nbr)
+            else:
+                self.X[i + 1] = ctx.runVertexForward(lambda t: torch.relu(t), nbr)
+
+    def Loss(self):
+        a = self.X[-1]
+        self.loss = torch.nn.functional.nll_loss(a.index_select(0, self.train_rows),
+                                                 self.L_GT.index_select(0, self.train_rows))
+        self.ctx.appendNNOp(a, self.loss)
+
+    def Update(self):
+        for p in self.params():
+            if p.W.grad is None:
+                continue
+            p.all_reduce_to_gradient(p.W.grad)
+            p.learn_with_decay_Adam()
+            p.next()
+
+    def run_epoch(self):
+        if self.epoch != 0:
+            for p in self.params():
+                p.zero_grad()
+        self.Forward()
+        self.Loss()
+        self.ctx.self_backward(True)
+        self.Update()
+        self.epoch += 1
+        return self.loss

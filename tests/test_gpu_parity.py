@@ -162,6 +162,22 @@ def test_golden_edge_ops(golden):
         close(dw, dw_o)
 
 
+def test_golden_dep_neighbor_single_gpu(golden):
+    """DistGPUGetDepNbrOp at P=1 (no communication): mirror rows and returned gradients vs the reference."""
+    from neutronstarlite_b200 import ops
+    from neutronstarlite_b200.exchange import GpuExchange
+    from neutronstarlite_b200.graph import HostGraph, PartitionedGraph
+    g = golden
+    if g.P != 1:
+        pytest.skip("single-partition case only (P>1 is covered by tests/test_multi_gpu.py)")
+    pg = PartitionedGraph(HostGraph(g.edges, g.V), 1, 0).generate_all(device=dev(), dist=True)
+    op = ops.DistGPUGetDepNbrOp(pg, None, exchange=GpuExchange(pg))
+    mirror = op.forward(up(g.mat(0, "X")))
+    assert np.array_equal(mirror.cpu().numpy(), g.mat(0, "dep_mirror"))
+    dx = op.backward(up(g.mat(0, "dep_Gm")))
+    close(dx.cpu().numpy(), g.mat(0, "dep_dX"))
+
+
 # ------------------------------------------------------------------------------------------------------------
 # (2) seeded random multigraphs against the C oracle
 # ------------------------------------------------------------------------------------------------------------

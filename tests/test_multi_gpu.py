@@ -43,6 +43,15 @@ def _worker(rank, world, port, case, transport, q):
             torch.cuda.synchronize()
             np.testing.assert_allclose(y.cpu().numpy(), ref_y, rtol=1e-4, atol=1e-5)
             np.testing.assert_allclose(dx.cpu().numpy(), ref_dx, rtol=1e-4, atol=2e-5)
+        # mirror fetch / return (DistGPUGetDepNbrOp) against the reference's DistGetDepNbrOp at the same P
+        dep = ops.DistGPUGetDepNbrOp(pg, None, exchange=ex)
+        mirror = dep.forward(x)
+        torch.cuda.synchronize()
+        assert np.array_equal(mirror.cpu().numpy(), z["r%d/dep_mirror" % rank].reshape(-1, F))
+        gm = torch.from_numpy(z["r%d/dep_Gm" % rank].reshape(-1, F)).to(dev)
+        dxm = dep.backward(gm)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dxm.cpu().numpy(), z["r%d/dep_dX" % rank].reshape(-1, F), rtol=1e-4, atol=2e-5)
         # a wider feature matrix (second width through the same exchange object)
         F2 = 40
         gen = torch.Generator().manual_seed(1)
