@@ -193,6 +193,9 @@ int nts_gather_rows(float *dst, const float *src, const nts_vid_t *rows, nts_vid
 /* dst[rows[k],:] += src[k,:]  (receiver-side add of partial gradients; rows must be unique) */
 int nts_scatter_add_rows(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows,
                          nts_vid_t feature_size, void *stream);
+/* same with vector red.global.add: rows may repeat (partials of several senders merged into one launch) */
+int nts_scatter_add_rows_atomic(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows,
+                                nts_vid_t feature_size, void *stream);
 
 /* ---- peer memory (CUDA IPC) for the NVLink exchange ------------------------------------------------------ */
 #define NTS_IPC_HANDLE_BYTES 64

@@ -387,6 +387,11 @@ int nts_scatter_add_rows(float *dst, const float *src, const nts_vid_t *rows, nt
   return move_rows<1>(dst, src, rows, nullptr, n_rows, nullptr, feature_size, as_stream(stream));
 }
 
+int nts_scatter_add_rows_atomic(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows,
+                                nts_vid_t feature_size, void *stream) {
+  return move_rows<2>(dst, src, rows, nullptr, n_rows, nullptr, feature_size, as_stream(stream));
+}
+
 // The edge count E_p = column_offset[batch_size] is read by the kernels on the device (the reference keeps
 // e_size on the host inside deviceCSC; its Cuda_Stream signatures do not pass it).
 int nts_scatter_src_mirror_to_msg(float *message, const float *src_mirror_feature, const nts_vid_t *row_indices,

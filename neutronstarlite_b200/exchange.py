@@ -20,7 +20,8 @@ Transports:
   "p2p"   no packing and no NCCL on the data path: every rank exports its [V_p, F] buffer through CUDA IPC and the
           RECEIVER pulls the rows it needs straight out of the peer's HBM over NVLink with `nts_gather_rows` on
           mapped peer pointers; completion is stream-ordered locally, cross-rank ordering uses system-scope flags
-          (`nts_signal_set` / `nts_signal_wait_geq`).  Chunk i+1 is pulled while chunk i aggregates.
+          (`nts_signal_set` / `nts_signal_wait_geq`).  The pulls overlap the local chunk's aggregation; all remote
+          chunks are then aggregated by ONE launch over a merged CSC (launch-bound regime at 8 GPUs).
 """
 from __future__ import annotations
 
@@ -88,6 +89,58 @@ class ExchangePlan:
             self.send_rows = [None]
         self.recv_total = sum(self.need_count[i] for i in range(P) if i != p)
         self.send_total = sum(self.send_count[j] for j in range(P) if j != p)
+        self._merge_remote()
+
+    def _merge_remote(self):
+        """One CSC over ALL remote chunks (sources = slots of the single receive staging buffer) and one compact CSR
+        over all remote chunks (rows = the send staging layout): the remote part of an aggregation is then ONE kernel
+        launch instead of P-1 (at 8 GPUs the per-chunk kernels are ~0.1-0.3 ms, i.e. launch-bound)."""
+        P, p, dev = self.P, self.p, self.device
+        chunks = self.pg.graph_chunks
+        self.recv_offs = np.concatenate([[0], np.cumsum([self.need_count[i] if i != p else 0 for i in range(P)])])
+        self.remote_edges = 0
+        self.remote_col_offset = self.remote_slots = self.remote_w = None
+        self.bwd_offsets = self.bwd_indices = self.bwd_w = None
+        self.send_rows_all = None
+        if P == 1:
+            return
+        Vp = self.pg.owned_vertices
+        dsts, slots, ws, b_off, b_idx, b_w = [], [], [], [], [], []
+        edge_base = 0
+        for i in range(P):
+            if i == p:
+                continue
+            c = chunks[i]
+            if c.edge_size:
+                co = self._arr(c, "column_offset").to(torch.int64)
+                dsts.append(torch.repeat_interleave(torch.arange(Vp, device=dev), co[1:] - co[:-1]))
+                slots.append(self.csc_slots[i].to(torch.int64) + int(self.recv_offs[i]))
+                ws.append(self._farr(c, "edge_weight_forward"))
+                b_idx.append(self._arr(c, "column_indices"))
+                b_w.append(self._farr(c, "edge_weight_backward"))
+            b_off.append(self.csr_offsets_compact[i][:-1].to(torch.int64) + edge_base)
+            edge_base += c.edge_size
+        self.remote_edges = edge_base
+        if edge_base:
+            dst = torch.cat(dsts)
+            order = torch.argsort(dst, stable=True)
+            self.remote_slots = torch.cat(slots)[order].to(torch.int32)
+            self.remote_w = torch.cat(ws)[order].contiguous()
+            col = torch.zeros(Vp + 1, dtype=torch.int64, device=dev)
+            col[1:] = torch.cumsum(torch.bincount(dst, minlength=Vp), 0)
+            self.remote_col_offset = col.to(torch.int32)
+            self.bwd_indices = torch.cat(b_idx).contiguous()
+            self.bwd_w = torch.cat(b_w).contiguous()
+        self.bwd_offsets = torch.cat(b_off + [torch.tensor([edge_base], dtype=torch.int64, device=dev)]).to(torch.int32)
+        rows = [self.send_rows[j] for j in range(P) if j != p and self.send_rows[j] is not None]
+        self.send_rows_all = torch.cat(rows).contiguous() if rows else torch.zeros(0, dtype=torch.int32, device=dev)
+
+    @staticmethod
+    def _farr(c, name):
+        g = getattr(c, name + "_gpu")
+        if g is not None:
+            return g
+        return torch.from_numpy(getattr(c, name))
 
     @staticmethod
     def _arr(c, name):
@@ -139,16 +192,12 @@ class GpuExchange:
             return ops.gather_by_dst_from_src(pg.graph_chunks[0], y, x)
         if self._p2p is not None:
             return self._forward_p2p(x, y)
-        # pack the rows every peer needs, exchange on the side stream
+        # pack the rows every peer needs (one launch over the concatenated row list), exchange on the side stream
         send = self._buf("fsend", plan.send_total, F)
         recv = self._buf("frecv", plan.recv_total, F)
-        pos = 0
-        for j in range(P):
-            n = plan.send_count[j]
-            if j != p and n:
-                _lib.call("nts_gather_rows", _ptr(send[pos:pos + n]), _ptr(x), _ptr(plan.send_rows[j]), n, F,
-                          cur.cuda_stream)
-                pos += n
+        if plan.send_total:
+            _lib.call("nts_gather_rows", _ptr(send), _ptr(x), _ptr(plan.send_rows_all), plan.send_total, F,
+                      cur.cuda_stream)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
             in_split = [plan.send_count[j] if j != p else 0 for j in range(P)]
@@ -159,14 +208,37 @@ class GpuExchange:
         ops.gather_by_dst_from_src(pg.graph_chunks[p], y, x)
         cur.wait_stream(self.comm_stream)
         recv.record_stream(cur)
-        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
-        for i in plan.ring():
-            c = pg.graph_chunks[i]
-            if c.edge_size == 0:
-                continue
-            seg = recv[int(offs[i]):int(offs[i + 1])]
-            self._aggregate_slots(c, plan.csc_slots[i], y, seg)
+        self._aggregate_remote(y, recv)
         return y
+
+    def _aggregate_remote(self, y, staged):
+        """All remote chunks in one launch: merged CSC whose indices are slots of the receive staging buffer."""
+        plan = self.plan
+        if not plan.remote_edges:
+            return
+        ev = ops._timer.bracket("fwd", staged.shape[1], plan.remote_edges, self.pg.owned_vertices) if ops._timer else None
+        if ev:
+            ev[0].record()
+        _lib.call("nts_segment_gather_sum", _ptr(staged), _ptr(y), _ptr(plan.remote_w), _ptr(plan.remote_slots),
+                  _ptr(plan.remote_col_offset), 0, self.pg.owned_vertices, plan.remote_edges, staged.shape[1],
+                  torch.cuda.current_stream().cuda_stream)
+        if ev:
+            ev[1].record()
+
+    def _partial_remote(self, out_rows, g):
+        """Partial gradients of the active sources of ALL remote chunks in one launch (merged compact CSR); the
+        output rows are laid out exactly like the send staging buffer."""
+        plan = self.plan
+        if not plan.remote_edges:
+            return
+        ev = ops._timer.bracket("bwd", g.shape[1], plan.remote_edges, out_rows.shape[0]) if ops._timer else None
+        if ev:
+            ev[0].record()
+        _lib.call("nts_segment_gather_sum", _ptr(g), _ptr(out_rows), _ptr(plan.bwd_w), _ptr(plan.bwd_indices),
+                  _ptr(plan.bwd_offsets), self.pg.graph_chunks[self.p].dst_range[0], out_rows.shape[0],
+                  plan.remote_edges, g.shape[1], torch.cuda.current_stream().cuda_stream)
+        if ev:
+            ev[1].record()
 
     def _aggregate_slots(self, c, slots, y, staged):
         """Chunk aggregation from a compact staging buffer: indices are slots, base 0."""
@@ -247,13 +319,7 @@ class GpuExchange:
         send = self._buf("bsend", plan.recv_total, F)
         recv = self._buf("brecv", plan.send_total, F)
         send.zero_()
-        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
-        for i in plan.ring():
-            c = pg.graph_chunks[i]
-            if c.edge_size == 0:
-                continue
-            seg = send[int(offs[i]):int(offs[i + 1])]
-            self._partial_compact(c, plan.csr_offsets_compact[i], seg, g)
+        self._partial_remote(send, g)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
             in_split = [plan.need_count[i] if i != p else 0 for i in range(P)]
@@ -263,13 +329,9 @@ class GpuExchange:
         ops.gather_by_src_from_dst(pg.graph_chunks[p], dx, g)   # local chunk overlaps with the transfer
         cur.wait_stream(self.comm_stream)
         recv.record_stream(cur)
-        pos = 0
-        for j in range(P):
-            n = plan.send_count[j]
-            if j != p and n:
-                _lib.call("nts_scatter_add_rows", _ptr(dx), _ptr(recv[pos:pos + n]), _ptr(plan.send_rows[j]), n, F,
-                          cur.cuda_stream)
-                pos += n
+        if plan.send_total:  # rows repeat across senders -> vector atomics, one launch
+            _lib.call("nts_scatter_add_rows_atomic", _ptr(dx), _ptr(recv), _ptr(plan.send_rows_all), plan.send_total, F,
+                      cur.cuda_stream)
         return dx
 
     def _partial_compact(self, c, offsets_compact, out_rows, g):
@@ -297,27 +359,20 @@ class GpuExchange:
         recv = self._buf("frecv", plan.recv_total, F)
         offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
         ring = plan.ring()
-        # pull chunk i+1 on the side stream while chunk i aggregates on the main stream
-        pulled = []
+        # pull every peer's rows on the side stream (NVLink loads by the receiver) while the local chunk aggregates
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
             for i in ring:
                 n = plan.need_count[i]
-                seg = recv[int(offs[i]):int(offs[i + 1])]
                 if n:
+                    seg = recv[int(offs[i]):int(offs[i + 1])]
                     w.wait_published(i, epoch, self.comm_stream)
                     _lib.call("nts_gather_rows", _ptr(seg), w.peer_ptr(i), _ptr(plan.need[i]), n, F,
                               self.comm_stream.cuda_stream)
-                ev = torch.cuda.Event()
-                ev.record(self.comm_stream)
-                pulled.append(ev)
             w.signal_consumed(epoch, self.comm_stream)
         recv.record_stream(self.comm_stream)
-        for k, i in enumerate(ring):
-            c = pg.graph_chunks[i]
-            cur.wait_event(pulled[k])
-            if c.edge_size:
-                self._aggregate_slots(c, plan.csc_slots[i], y, recv[int(offs[i]):int(offs[i + 1])])
+        cur.wait_stream(self.comm_stream)
+        self._aggregate_remote(y, recv)
         return y
 
     def _backward_p2p(self, g, dx):
@@ -331,26 +386,29 @@ class GpuExchange:
         epoch = w.begin(cur)                       # peers are done with what I published last time
         win = w.window_rows(plan.recv_total, F)
         win.zero_()
-        for i in plan.ring():
-            c = pg.graph_chunks[i]
-            if c.edge_size:
-                self._partial_compact(c, plan.csr_offsets_compact[i], win[int(offs[i]):int(offs[i + 1])], g)
+        self._partial_remote(win, g)
         w.commit(epoch, cur)
-        ops.gather_by_src_from_dst(pg.graph_chunks[p], dx, g)
-        # pull from every peer j the slice it computed for me: rows offs_j[p] .. of ITS window
+        # every peer j computed a slice for me inside ITS window: copy it out of peer memory over NVLink on the side
+        # stream (overlaps the local chunk), then one scatter-add launch once the local chunk is done with dx
+        recv = self._buf("brecv", plan.send_total, F)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            for j in plan.ring():
+            pos = 0
+            for j in range(P):
                 n = plan.send_count[j]
-                if n:
-                    w.wait_published(j, epoch, self.comm_stream)
-                    src = w.peer_ptr(j) + int(w.peer_bwd_offset[j]) * F * 4
-                    tmp = self._buf("brecv%d" % j, n, F)
-                    _lib.call("nts_memcpy_d2d", _ptr(tmp), src, n * F * 4, self.comm_stream.cuda_stream)
-                    _lib.call("nts_scatter_add_rows", _ptr(dx), _ptr(tmp), _ptr(plan.send_rows[j]), n, F,
-                              self.comm_stream.cuda_stream)
+                if j == p or not n:
+                    continue
+                w.wait_published(j, epoch, self.comm_stream)
+                src = w.peer_ptr(j) + int(w.peer_bwd_offset[j]) * F * 4
+                _lib.call("nts_memcpy_d2d", _ptr(recv[pos:pos + n]), src, n * F * 4, self.comm_stream.cuda_stream)
+                pos += n
             w.signal_consumed(epoch, self.comm_stream)
+        recv.record_stream(self.comm_stream)
+        ops.gather_by_src_from_dst(pg.graph_chunks[p], dx, g)
         cur.wait_stream(self.comm_stream)
+        if plan.send_total:
+            _lib.call("nts_scatter_add_rows_atomic", _ptr(dx), _ptr(recv), _ptr(plan.send_rows_all), plan.send_total, F,
+                      cur.cuda_stream)
         return dx
 
 

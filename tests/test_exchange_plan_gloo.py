@@ -73,6 +73,14 @@ def _worker(rank, world, port, case, q):
             Y += _gather_sum(c.column_offset, plan.csc_slots[i].numpy(), c.edge_weight_forward, staged, Vp)
         ref_Y = z["r%d/gcn_Y" % rank].reshape(-1, F)
         np.testing.assert_allclose(Y, ref_Y, rtol=1e-5, atol=1e-5)
+        # the merged remote CSC (one launch for all remote chunks) gives the same result
+        if plan.remote_edges:
+            staged_all = np.concatenate([recv[i].numpy() for i in range(P) if i != rank])
+            c = pg.graph_chunks[rank]
+            Y2 = _gather_sum(c.column_offset, c.row_indices - c.src_range[0], c.edge_weight_forward, Xl, Vp)
+            Y2 += _gather_sum(plan.remote_col_offset.numpy(), plan.remote_slots.numpy(), plan.remote_w.numpy(),
+                              staged_all, Vp)
+            np.testing.assert_allclose(Y2, ref_Y, rtol=1e-5, atol=1e-5)
         # ---- backward: compact partials per remote chunk, returned to the owners, unique-row scatter-add
         parts = []
         for i in range(P):
@@ -84,6 +92,13 @@ def _worker(rank, world, port, case, q):
             part = _gather_sum(offc, c.column_indices - c.dst_range[0], c.edge_weight_backward, Gl, plan.need_count[i])
             parts.append(torch.from_numpy(part.astype(np.float32)))
         got = _a2a(parts, [plan.send_count[j] if j != rank else 0 for j in range(P)], F)
+        # merged compact CSR == concatenation of the per-chunk partials, in send-staging order
+        if plan.remote_edges:
+            merged = _gather_sum(plan.bwd_offsets.numpy(), plan.bwd_indices.numpy().view(np.uint32) - pg.graph_chunks[rank].dst_range[0],
+                                 plan.bwd_w.numpy(), Gl, plan.recv_total)
+            np.testing.assert_allclose(merged, np.concatenate([t.numpy() for t in parts]), rtol=1e-5, atol=1e-6)
+            rows_all = np.concatenate([plan.send_rows[j].numpy() for j in range(P) if j != rank])
+            assert np.array_equal(rows_all, plan.send_rows_all.numpy())
         c = pg.graph_chunks[rank]
         dX = _gather_sum(c.row_offset, c.column_indices - c.dst_range[0], c.edge_weight_backward, Gl, Vp)
         for j in range(P):
