@@ -51,7 +51,11 @@ class NtsContext:
         op = op_class(partitioned_graph, active, **op_kwargs)
         if f_input2 is None:
             out = op.forward(f_input)
-            out.requires_grad_(True)  # NewKeyTensor: outputs are leaves that collect gradients
+            # NewKeyTensor: outputs are leaves that collect gradients.  The one exception: a graph op recorded as
+            # the FIRST tape entry is never back-propagated (self_backward stops at it, ntsContext.hpp:283), so
+            # nobody ever reads its output gradient - do not make torch compute it (saves the dY = dH.W^T GEMM of
+            # the input layer; parameter gradients are unaffected).
+            out.requires_grad_(bool(self.tape) or not self.training)
             if self.training:
                 self.tape.append(_Entry(GRAPHOP, op, f_input, out))
         else:
@@ -95,7 +99,9 @@ class NtsContext:
         assert self.training and self.tape
         top = self.tape[-1]
         top.output.backward(torch.ones_like(top.output), retain_graph=retain_graph)
-        if len(self.tape) >= 2:
+        if len(self.tape) >= 2 and not self.sum_fanout_grads:
+            # (in sum mode the entry fetches the same tensor through output.grad below; assigning it here as well
+            #  would count it twice)
             self.tape[-2].grad = top.input.grad
         self.tape.pop()
         while len(self.tape) > 1 or (len(self.tape) == 1 and self.tape[-1].kind == NNOP):

@@ -8,7 +8,8 @@
 extern "C" {
 
 void *refcuda_stream_create() { return new Cuda_Stream(); }
-void *refcuda_stream_handle(void *s) { return (void *)static_cast<Cuda_Stream *>(s)->getStream(); }
+// (Cuda_Stream::getStream() is declared but never defined in the reference: read the public member instead)
+void *refcuda_stream_handle(void *s) { return (void *)static_cast<Cuda_Stream *>(s)->stream; }
 void refcuda_stream_sync(void *s) { static_cast<Cuda_Stream *>(s)->CUDA_DEVICE_SYNCHRONIZE(); }
 
 // optim = 0: aggregate_kernel_from_src_with_weight (global atomicAdd per edge element), the path
