@@ -333,6 +333,9 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uin
     s.vec = 2;
   else
     s.vec = 1;
+  if (heads > 1) // a head's columns must be a whole number of vectors
+    while (s.vec > 1 && (F / heads) % s.vec != 0)
+      s.vec >>= 1;
   const uint32_t nvec = F / s.vec;
   const uint32_t chunks = (nvec + 31) / 32;
   const uint32_t kmax = (s.vec == 4) ? 4 : 5;
@@ -426,12 +429,6 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   }
   LaunchShape s = pick_shape(in, out, F, heads);
   if (heads > 1) {
-    // the head width must be a whole number of vectors; fall back to narrower vectors if it is not
-    while (s.vec > 1 && (F / heads) % s.vec != 0) {
-      s.vec >>= 1;
-      s.tile_vecs = (F / s.vec) / heads;
-      s.k = (int)((s.tile_vecs + 31) / 32);
-    }
     NTS_ARG_CHECK(s.k >= 1 && s.k <= 5, "head width too large for one column tile");
     s.minb = 1;
     int budget = 40 / (s.k * s.vec);

@@ -368,7 +368,7 @@ def test_properties_at_scale():
                               getattr(dc, name + "_gpu").cpu().numpy().view(np.uint32)), name
 
 
-@pytest.mark.parametrize("H,D", [(1, 24), (2, 16), (8, 64), (8, 8), (3, 5)])
+@pytest.mark.parametrize("H,D", [(1, 24), (2, 16), (8, 64), (8, 8), (3, 5), (4, 2), (4, 1)])
 def test_multi_head_fused_aggregation(H, D):
     """Fused GAT aggregation with [E, H] attention weights (config D of BASELINE.json uses 8 heads): head h scales
     columns [h*D, (h+1)*D).  Oracle: the single-head C loop applied per head; backward against the numpy restatement
