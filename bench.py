@@ -37,7 +37,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="reddit")
-    ap.add_argument("--transport", default=os.environ.get("NTS_TRANSPORT", "nccl"), choices=["nccl", "p2p"])
+    ap.add_argument("--transport", default=os.environ.get("NTS_TRANSPORT", "auto"), choices=["auto", "nccl", "p2p"],
+                    help="partition-boundary exchange: p2p = CUDA-IPC peer-memory pull over NVLink, nccl = all-to-all; "
+                         "auto = p2p, falling back to nccl if peer mappings cannot be set up")
     ap.add_argument("--variant", type=int, default=0, help="aggregation kernel variant (0 auto, 1 shuffle, 2 bulk)")
     ap.add_argument("--edges-per-warp", type=int, default=0)
     ap.add_argument("--drop-rate", type=float, default=0.5)
@@ -240,8 +242,25 @@ def main():
     v0, v1 = int(po[rank]), int(po[rank + 1])
     feats, labels, mask = synth.features_labels_mask(V, layers[0], layers[-1], dev, rows=(v0, v1))
     op_kwargs = {}
+    transport = args.transport
     if world > 1:
-        op_kwargs["exchange"] = GpuExchange(pg, transport=args.transport)
+        if transport == "auto":
+            # every rank must take the same branch: agree on whether the IPC windows could be set up
+            try:
+                ex = GpuExchange(pg, transport="p2p")
+                ok = torch.ones(1, device=dev)
+            except Exception as exc:  # noqa: BLE001 - any failure means "no peer access here"
+                sys.stderr.write("bench.py: p2p exchange unavailable (%r), using nccl\n" % (exc,))
+                ex, ok = None, torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1:
+                ex = GpuExchange(pg, transport="nccl")
+                transport = "nccl"
+            else:
+                transport = "p2p"
+        else:
+            ex = GpuExchange(pg, transport=transport)
+        op_kwargs["exchange"] = ex
     model = GCNImpl(pg, layers, feats, labels, mask, drop_rate=args.drop_rate, op_kwargs=op_kwargs)
 
     def barrier():
@@ -380,7 +399,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "epochs_per_sec": 1e3 / ms_step,
             "config": {"workload": _workload_name(args.workload, V, E_total, layers),
-                       "parallelism": "graph-partition x%d (reference partitioner), %s exchange" % (world, args.transport)
+                       "parallelism": "graph-partition x%d (reference partitioner), %s exchange" % (world, transport)
                        if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (features %.0f MB, graph arrays %.0f MB per rank)" % (
                            feats.numel() * 4 / 1e6, pg.owned_edges * 16 / 1e6),
