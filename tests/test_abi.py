@@ -46,3 +46,23 @@ def test_argument_errors_are_reported_not_swallowed():
     assert rc != 0
     assert b"variant" in lib.nts_last_error()
     assert lib.nts_aggregate_set_variant(0, 0) == 0
+
+
+def test_bench_reference_arm_prints_the_contract_keys():
+    """`bench.py --impl reference` (CPU only: the unmodified reference GCNCPU, or the C port when oracle/_ref is
+    absent) on the tiny workload: one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "1", "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-800:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
