@@ -451,8 +451,11 @@ def reference_gpu_kernels(pg, feats, layers, torch):
             b.record(ext)
             ref.refcuda_stream_sync(cs)
             torch.cuda.synchronize()
-            if it > 0:
-                times.append(a.elapsed_time(b))
+            ms = a.elapsed_time(b)
+            if it > 0 or ms > 2000.0:   # keep the baseline bounded: a launch slower than 2 s is measured once
+                times.append(ms)
+            if ms > 2000.0:
+                break
         mine = torch.zeros_like(y)
         ops.gather_by_dst_from_src(c, mine, x)
         torch.cuda.synchronize()
