@@ -240,17 +240,6 @@ class GpuExchange:
         if ev:
             ev[1].record()
 
-    def _aggregate_slots(self, c, slots, y, staged):
-        """Chunk aggregation from a compact staging buffer: indices are slots, base 0."""
-        ev = ops._timer.bracket("fwd", staged.shape[1], c.edge_size, c.batch_size_forward) if ops._timer else None
-        if ev:
-            ev[0].record()
-        _lib.call("nts_segment_gather_sum", _ptr(staged), _ptr(y), _ptr(c.edge_weight_forward_gpu), _ptr(slots),
-                  _ptr(c.column_offset_gpu), 0, c.batch_size_forward, c.edge_size, staged.shape[1],
-                  torch.cuda.current_stream().cuda_stream)
-        if ev:
-            ev[1].record()
-
     # ---- mirror fetch / return (DistGPUGetDepNbrOp, core/ntsDistGPUGraphOp.hpp:48-143) ----------------------------
     def fetch_mirrors(self, x):
         """mirror[MirrorIndex[s], :] = X[s, :] for every source s of a local in-edge, [owned_mirrors, F].
@@ -333,16 +322,6 @@ class GpuExchange:
             _lib.call("nts_scatter_add_rows_atomic", _ptr(dx), _ptr(recv), _ptr(plan.send_rows_all), plan.send_total, F,
                       cur.cuda_stream)
         return dx
-
-    def _partial_compact(self, c, offsets_compact, out_rows, g):
-        ev = ops._timer.bracket("bwd", g.shape[1], c.edge_size, out_rows.shape[0]) if ops._timer else None
-        if ev:
-            ev[0].record()
-        _lib.call("nts_segment_gather_sum", _ptr(g), _ptr(out_rows), _ptr(c.edge_weight_backward_gpu),
-                  _ptr(c.column_indices_gpu), _ptr(offsets_compact), c.dst_range[0], out_rows.shape[0],
-                  c.edge_size, g.shape[1], torch.cuda.current_stream().cuda_stream)
-        if ev:
-            ev[1].record()
 
     # ---- peer-memory transport ------------------------------------------------------------------------------------
     def _forward_p2p(self, x, y):

@@ -115,3 +115,25 @@ def test_gat_epoch_matches_torch_autograd(heads):
     for mine, ref in zip(model.P + model.al + model.ar, Ws + als + ars):
         torch.testing.assert_close(mine.W.grad, ref.grad, rtol=2e-3, atol=2e-6)
     model.Update()
+
+
+def test_bench_prints_the_contract_line_on_a_tiny_workload():
+    """`bench.py` (our arm) end to end on the tiny workload: one JSON line with every key of the bench contract,
+    kernels of libnts_b200 actually launched, roofline and e2e present."""
+    import json
+    import os
+    import subprocess
+    import sys
+    dev()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "tiny", "--steps", "3",
+                          "--warmup", "3", "--no-cpu-baseline", "--no-ref-gpu"], stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert key in line, key
+    assert line["gpu_launches"] >= 9 and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["achieved"] > 0
