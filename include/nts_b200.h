@@ -173,6 +173,33 @@ int nts_aggregate_dst_fuse_weight_backward_heads(float *mirror_grad, float *edge
                                                  const nts_vid_t *mirror_index, nts_vid_t batch_size,
                                                  nts_vid_t feature_size, nts_vid_t heads, void *stream);
 
+/* ---- fully fused GAT layer (K7): edge logits / attention are never materialised ---------------------------------
+ * The flow of toolkits/GAT_CPU_DIST_OPTM.hpp:196-241 (per-vertex scores -> leaky_relu -> edge softmax ->
+ * DistAggregateDstFuseWeight) with a[e,h] = softmax_seg(leaky_relu(src_score[slot(e),h] + dst_score[dst(e),h]))
+ * recomputed inside the kernels; slot(e) = mirror_index[row_indices[e]], head h owns columns [h*D,(h+1)*D), D <= 512.
+ *   stats    : seg_max[d,h], seg_sum[d,h]                                   ([batch_size, heads] each)
+ *   forward  : output[d, hD+c] += sum_e a[e,h] * mirror[slot(e), hD+c]
+ *   backward : mirror_grad[slot,hD+c] += a*g[d,hD+c];  src_score_grad[slot,h] += dpre;  dst_score_grad[d,h] += dpre
+ *              with dpre = a*(<mirror[slot,h],g[d,h]> - out_dot_grad[d,h]) * leaky_relu'(pre) and
+ *              out_dot_grad[d,h] = <output[d,h], g[d,h]> supplied by the caller (a per-vertex dot product).
+ *   The three gradient outputs must be zeroed by the caller. */
+int nts_gat_softmax_stats(float *seg_max, float *seg_sum, const float *src_score, const float *dst_score,
+                          const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                          const nts_vid_t *mirror_index, nts_vid_t batch_size, nts_vid_t heads,
+                          float negative_slope, void *stream);
+int nts_gat_fused_aggregate_forward(const float *mirror, float *output, const float *src_score,
+                                    const float *dst_score, const float *seg_max, const float *seg_sum,
+                                    const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                    const nts_vid_t *mirror_index, nts_vid_t batch_size, uint64_t n_edges,
+                                    nts_vid_t feature_size, nts_vid_t heads, float negative_slope, void *stream);
+int nts_gat_fused_aggregate_backward(float *mirror_grad, float *src_score_grad, float *dst_score_grad,
+                                     const float *mirror, const float *src_score, const float *dst_score,
+                                     const float *seg_max, const float *seg_sum, const float *out_dot_grad,
+                                     const float *dst_grad, const nts_vid_t *row_indices,
+                                     const nts_vid_t *column_offset, const nts_vid_t *mirror_index,
+                                     nts_vid_t batch_size, nts_vid_t feature_size, nts_vid_t heads,
+                                     float negative_slope, void *stream);
+
 /* ---- (vid,row) message records: the reference's host-staged exchange format (comm/network.h:143-149) ---
  * record k = { uint32 vid; float row[feature_size]; }, read through mapped pinned host memory. */
 /* mirror[vid - partition_start,:] = record.row if vid in [partition_start, partition_end)

@@ -80,7 +80,8 @@ def build(force=False, verbose=False):
                   "-c", s, "-o", o], verbose, log)
             relink = True
     if relink or not os.path.exists(LIB):
-        _run([nvcc, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lgomp"], verbose, log)
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs +
+             ["-Xcompiler", "-fopenmp", "-lgomp"], verbose, log)
     with open(os.path.join(LIBDIR, "build.log"), "a") as f:
         f.write("\n".join(log))
     return LIB

@@ -10,17 +10,18 @@ from __future__ import annotations
 
 import torch
 
-GRAPHOP, BIGRAPHOP, NNOP = "GRAPHOP", "BIGRAPHOP", "NNOP"
+GRAPHOP, BIGRAPHOP, NGRAPHOP, NNOP = "GRAPHOP", "BIGRAPHOP", "NGRAPHOP", "NNOP"
 
 
 class _Entry:
-    __slots__ = ("kind", "op", "input", "output", "o_id", "i_id1", "i_id2", "grad")
+    __slots__ = ("kind", "op", "input", "output", "o_id", "i_id1", "i_id2", "i_ids", "grad")
 
-    def __init__(self, kind, op, inp, out, i_id2=None):
+    def __init__(self, kind, op, inp, out, i_id2=None, i_ids=None):
         self.kind, self.op, self.input, self.output = kind, op, inp, out
         self.o_id = out.data_ptr()
         self.i_id1 = inp.data_ptr()
         self.i_id2 = i_id2
+        self.i_ids = i_ids
         self.grad = None
 
 
@@ -62,6 +63,16 @@ class NtsContext:
             out = op.forward(f_input, f_input2)
             out.requires_grad_(True)
             self.tape.append(_Entry(BIGRAPHOP, op, f_input, out, f_input2.data_ptr()))
+        return out
+
+    def runGraphOpN(self, op_class, partitioned_graph, active, inputs, **op_kwargs):
+        """Additive generalisation of the two-input form (ntsContext.hpp:130-149) to N tensor inputs: the operator's
+        `backward(grad)` returns one gradient per input, each routed to the tape entry that produced that input."""
+        op = op_class(partitioned_graph, active, **op_kwargs)
+        out = op.forward(*inputs)
+        out.requires_grad_(True)
+        if self.training:
+            self.tape.append(_Entry(NGRAPHOP, op, inputs[0], out, i_ids=[t.data_ptr() for t in inputs]))
         return out
 
     def runVertexForward(self, vertexforward, nbr_input, vtx_input=None):
@@ -111,7 +122,14 @@ class NtsContext:
                 e.grad = e.output.grad
             elif self.sum_fanout_grads and e.kind != NNOP and e.output.grad is not None:
                 e.grad = e.grad + e.output.grad
-            if e.kind in (GRAPHOP, BIGRAPHOP):
+            if e.kind == NGRAPHOP:
+                grads = e.op.backward(e.grad)
+                for ptr, g_in in zip(e.i_ids, grads):
+                    k = self._producer_of(ptr, idx)
+                    if k >= 0:
+                        prev = self.tape[k].grad
+                        self.tape[k].grad = g_in if prev is None or prev.dim() < 2 else prev + g_in
+            elif e.kind in (GRAPHOP, BIGRAPHOP):
                 g_in = e.op.backward(e.grad)
                 k = self._producer_of(e.i_id1, idx)
                 if k >= 0:

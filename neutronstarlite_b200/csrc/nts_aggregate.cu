@@ -115,19 +115,37 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 
 constexpr int kWarpsPerBlock = 8;
 
+// Fused GAT attention (K7): instead of loading a per-edge weight, recompute it from per-vertex scores
+//   a[e,h] = exp(leaky_relu(s[slot(e),h] + d[row,h]) - m[row,h]) / z[row,h]      (column tile t = head h)
+// m / z are the per-(destination, head) softmax statistics produced by gat_softmax_stats_kernel.
+struct AttParams {
+  const float *s; // [M, H] source scores (mirror rows)
+  const float *d; // [V, H] destination scores
+  const float *m; // [V, H] segment max of the logits
+  const float *z; // [V, H] segment sum of exp(logit - m)
+  float slope;    // leaky_relu negative slope
+};
+__device__ __forceinline__ float att_weight(float s, float d, float m, float inv_z, float slope) {
+  float x = s + d;
+  x = x > 0.f ? x : x * slope;
+  return expf(x - m) * inv_z;
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------
 // VEC  : floats per vector load (1, 2, 4); feature_size % VEC == 0 and rows VEC*4-byte aligned
 // K    : vector chunks per lane per column tile (a tile covers K*32*VEC floats)
 // U    : edges loaded before the FMAs start (memory-level parallelism = U*K loads per lane)
 // BULK : stage index/weight tiles with cp.async.bulk + mbarrier (variant 2)
 // MINB : minimum resident CTAs per SM handed to __launch_bounds__ (register cap = 65536 / (256*MINB))
-template <int VEC, int K, int U, bool BULK, int MINB = 1>
+// ATT  : weights are recomputed from attention scores (AttParams) instead of loaded (fused GAT, K7)
+template <int VEC, int K, int U, bool BULK, int MINB = 1, bool ATT = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     segment_gather_sum_kernel(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ w,
                               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
                               const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
                               uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
-                              uint32_t tile_major, uint32_t w_stride) {
+                              uint32_t tile_major, uint32_t w_stride, AttParams att) {
+  static_assert(!(ATT && BULK), "attention weights are not bulk-staged");
   using V = typename Vec<VEC>::type;
   const uint32_t n_edges = (uint32_t)n_edges64;
   const uint32_t lane = threadIdx.x & 31;
@@ -212,6 +230,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   for (int k = 0; k < K; k++)
     zero_vec(acc[k]);
 
+  // per-row attention constants of head `tile` (ATT only)
+  float att_d = 0.f, att_m = 0.f, att_iz = 0.f;
+  auto load_att_row = [&]() {
+    if constexpr (ATT) {
+      const size_t o = (size_t)row * w_stride + tile;
+      att_d = __ldg(att.d + o);
+      att_m = __ldg(att.m + o);
+      att_iz = 1.f / __ldg(att.z + o);
+    }
+  };
+  load_att_row();
+
   auto flush = [&](bool whole) {
     V *o = reinterpret_cast<V *>(out + (size_t)row * F) + c0;
 #pragma unroll
@@ -233,6 +263,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
       row_end = __ldg(off + row + 1);
     } while (ee >= row_end);
     row_started_inside = true;
+    load_att_row();
   };
 
   if constexpr (BULK) {
@@ -248,7 +279,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
       if (lane < cnt) {
         uint32_t id = __ldg(idx + e + lane);
         my_src = slot_of ? __ldg(slot_of + id) : id - base;
-        if (w) // multi-head weights [E, H]: column tile t is head t (w_stride = H), else one weight per edge
+        if constexpr (ATT)
+          my_w = __ldg(att.s + (size_t)my_src * w_stride + tile); // source score of this edge for head `tile`
+        else if (w) // multi-head weights [E, H]: column tile t is head t (w_stride = H), else one weight per edge
           my_w = __ldg(w + (size_t)(e + lane) * w_stride + (w_stride > 1 ? tile : 0u));
       }
     }
@@ -279,10 +312,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
         const uint32_t ee = e + j + u;
         if (ee >= row_end)
           advance(ee);
+        const float wq = ATT ? att_weight(wu[u], att_d, att_m, att_iz, att.slope) : wu[u];
 #pragma unroll
         for (int k = 0; k < K; k++)
           if (act[k])
-            fma_vec(acc[k], wu[u], v[u][k]);
+            fma_vec(acc[k], wq, v[u][k]);
       }
     }
     // remainder (< U edges)
@@ -306,10 +340,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
       const uint32_t ee = e + j;
       if (ee >= row_end)
         advance(ee);
+      const float wq = ATT ? att_weight(wj, att_d, att_m, att_iz, att.slope) : wj;
 #pragma unroll
       for (int k = 0; k < K; k++)
         if (act[k])
-          fma_vec(acc[k], wj, v1[k]);
+          fma_vec(acc[k], wq, v1[k]);
     }
   }
   // last row of the quantum: whole only if it started inside and also ends at/before e1
@@ -380,10 +415,13 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uin
   return s;
 }
 
+static const AttParams kNoAtt = {nullptr, nullptr, nullptr, nullptr, 0.f};
+
 template <int VEC, int K, int U, int MINB>
 static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float *out, const float *w,
                         const uint32_t *idx, const uint32_t *off, const uint32_t *slot_of, uint32_t base,
-                        uint32_t n_rows, uint64_t n_edges, uint32_t F, uint32_t Q, cudaStream_t st) {
+                        uint32_t n_rows, uint64_t n_edges, uint32_t F, uint32_t Q, cudaStream_t st,
+                        const AttParams *att = nullptr) {
   const uint64_t quanta = (n_edges + Q - 1) / Q;
   uint64_t warps;
   if (sh.tile_major)
@@ -394,6 +432,18 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
   NTS_ARG_CHECK(blocks <= 0x7fffffffull, "aggregation grid too large");
   g_last_grid = (int)blocks;
   g_last_block = kWarpsPerBlock * 32;
+  if (att) {
+    if constexpr (MINB == 1) { // attention kernels exist for the untuned occupancy points only
+      g_last_smem = 0;
+      segment_gather_sum_kernel<VEC, K, U, false, 1, true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+          in, out, nullptr, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
+          sh.w_stride, *att);
+      NTS_LAUNCH_CHECK();
+      return 0;
+    } else {
+      return fail(-1, "no attention kernel for this occupancy point", __FILE__, __LINE__);
+    }
+  }
   if (bulk) {
     size_t span_cap = (size_t)kWarpsPerBlock * Q + 8;
     size_t smem = 16 + 2 * span_cap * 4;
@@ -401,12 +451,13 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
     NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_last_smem = (int)smem;
     kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F,
-                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major, sh.w_stride);
+                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major, sh.w_stride,
+                                                              kNoAtt);
   } else {
     g_last_smem = 0;
     segment_gather_sum_kernel<VEC, K, U, false, MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
         in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
-        sh.w_stride);
+        sh.w_stride, kNoAtt);
   }
   NTS_LAUNCH_CHECK();
   return 0;
@@ -414,21 +465,28 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
 
 #define NTS_CASE(V_, K_, U_, B_)                                                                               \
   if (s.vec == V_ && s.k == K_ && s.u == U_ && s.minb == B_)                                                    \
-    return launch_shape<V_, K_, U_, B_>(bulk, s, in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, st);
+    return launch_shape<V_, K_, U_, B_>(bulk, s, in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, st, att);
 
 static int segment_gather_sum(const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *off,
                               const uint32_t *slot_of, uint32_t base, uint32_t n_rows, uint64_t n_edges, uint32_t F,
-                              cudaStream_t st, uint32_t heads = 1) {
+                              cudaStream_t st, uint32_t heads = 1, const AttParams *att = nullptr) {
   if (n_rows == 0 || n_edges == 0 || F == 0)
     return 0;
   NTS_ARG_CHECK(in && out && idx && off, "null pointer passed to segment_gather_sum");
   NTS_ARG_CHECK(n_edges < 0xffffffffull, "chunk edge count must fit uint32 offsets");
-  if (heads > 1) {
+  if (heads > 1 && !att) {
     NTS_ARG_CHECK(w != nullptr, "multi-head aggregation needs the [E, heads] weight matrix");
     NTS_ARG_CHECK(F % heads == 0, "feature_size must be a multiple of heads");
   }
   LaunchShape s = pick_shape(in, out, F, heads);
-  if (heads > 1) {
+  if (att && heads == 1) { // single head: still one column tile per head so the per-row constants are per tile
+    s.tiles = 1;
+    s.tile_major = 0;
+    s.tile_vecs = F / s.vec;
+    s.k = (int)((s.tile_vecs + 31) / 32);
+    s.w_stride = 1;
+  }
+  if (heads > 1 || att) {
     NTS_ARG_CHECK(s.k >= 1 && s.k <= 5, "head width too large for one column tile");
     s.minb = 1;
     int budget = 40 / (s.k * s.vec);
@@ -443,7 +501,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   }
   Q = (Q + 31u) & ~31u;
   int variant = g_variant == 0 ? 2 : g_variant; // measured on B200: bulk-staged indices are ~15-20% faster
-  bool bulk = variant == 2 && heads <= 1; // [E, H] weights are read per lane + shuffled, not bulk-staged
+  bool bulk = variant == 2 && heads <= 1 && !att; // [E, H] / attention weights are not bulk-staged
   // the bulk copies need 16-byte aligned index/weight arrays (cudaMalloc gives 256)
   if (bulk && !(aligned_to(idx, 16) && (!w || aligned_to(w, 16)))) {
     bulk = false;
@@ -514,6 +572,18 @@ int nts_segment_gather_sum_heads(const float *input, float *output, const float 
   NTS_ARG_CHECK(heads >= 1, "heads must be >= 1");
   return nts::segment_gather_sum(input, output, weight, indices, offsets, slot_of, index_base, n_rows, n_edges,
                                  feature_size, nts::as_stream(stream), heads);
+}
+
+int nts_gat_fused_aggregate_forward(const float *mirror, float *output, const float *src_score,
+                                    const float *dst_score, const float *seg_max, const float *seg_sum,
+                                    const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                    const nts_vid_t *mirror_index, nts_vid_t batch_size, uint64_t n_edges,
+                                    nts_vid_t feature_size, nts_vid_t heads, float negative_slope, void *stream) {
+  NTS_ARG_CHECK(heads >= 1 && feature_size % heads == 0, "feature_size must be a multiple of heads");
+  NTS_ARG_CHECK(src_score && dst_score && seg_max && seg_sum && mirror_index, "null pointer passed to fused GAT forward");
+  nts::AttParams att = {src_score, dst_score, seg_max, seg_sum, negative_slope};
+  return nts::segment_gather_sum(mirror, output, nullptr, row_indices, column_offset, mirror_index, 0, batch_size,
+                                 n_edges, feature_size, nts::as_stream(stream), heads, &att);
 }
 
 int nts_gather_by_dst_from_src(const float *input, float *output, const float *weight_forward,

@@ -305,6 +305,120 @@ __global__ void __launch_bounds__(kThreads)
   } // quantum loop
 }
 
+// ---- fully fused GAT layer (K7): attention logits are never materialised ------------------------------------------
+//   logit[e,h] = leaky_relu(s[slot(e),h] + d[dst(e),h]);  a = softmax over the destination segment
+// stats kernel: seg_max[d,h], seg_sum[d,h] (sum of exp(logit - max)); empty segments get (0, 1).
+__device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+__global__ void __launch_bounds__(kThreads)
+    gat_softmax_stats_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum, const float *__restrict__ s_att,
+                             const float *__restrict__ d_att, const uint32_t *__restrict__ row_idx,
+                             const uint32_t *__restrict__ off, const uint32_t *__restrict__ mirror_index,
+                             uint32_t n_rows, uint32_t H, float slope) {
+  __shared__ float scratch[kWarps];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t r0 = blockIdx.x * kRowsPerCta;
+  const uint32_t r1 = min(n_rows, r0 + kRowsPerCta);
+  for (uint32_t r = r0; r < r1; r++) {
+    const uint32_t b = __ldg(off + r), e = __ldg(off + r + 1);
+    const uint32_t deg = e - b;
+    const bool hub = deg > kHubDegree; // block-uniform
+    if (!hub && ((r - r0) % kWarps) != wid)
+      continue;
+    const uint32_t tid = hub ? threadIdx.x : lane;
+    const uint32_t nthr = hub ? kThreads : 32;
+    for (uint32_t h = 0; h < H; h++) {
+      if (deg == 0) {
+        if (tid == 0) {
+          seg_max[(size_t)r * H + h] = 0.f;
+          seg_sum[(size_t)r * H + h] = 1.f;
+        }
+        continue;
+      }
+      const float dv = __ldg(d_att + (size_t)r * H + h);
+      float mx = -INFINITY;
+      for (uint32_t i = tid; i < deg; i += nthr) {
+        const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+        mx = fmaxf(mx, leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope));
+      }
+      mx = hub ? block_reduce<true>(mx, scratch) : warp_max(mx);
+      float sum = 0.f;
+      for (uint32_t i = tid; i < deg; i += nthr) {
+        const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+        sum += expf(leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope) - mx);
+      }
+      sum = hub ? block_reduce<false>(sum, scratch) : warp_sum(sum);
+      if (tid == 0) {
+        seg_max[(size_t)r * H + h] = mx;
+        seg_sum[(size_t)r * H + h] = sum;
+      }
+    }
+  }
+}
+
+// backward of the fused layer, one pass over the edges:
+//   a        = exp(logit - m) / z                              (recomputed)
+//   d_a      = < mirror[slot, head h], g[dst, head h] >        (warp-shuffle reduction)
+//   d_logit  = a * (d_a - <out[dst,h], g[dst,h]>)              (softmax backward; the segment sum is a per-vertex dot)
+//   d_pre    = d_logit * leaky_relu'(pre)
+//   s_grad[slot,h] += d_pre (atomic),  d_grad[dst,h] += d_pre (per-row register sum, one atomic per row/quantum)
+//   mirror_grad[slot, head h] += a * g[dst, head h]            (vector red)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    gat_fused_backward_kernel(float *__restrict__ mirror_grad, float *__restrict__ s_grad, float *__restrict__ d_grad,
+                              const float *__restrict__ mirror, const float *__restrict__ s_att,
+                              const float *__restrict__ d_att, const float *__restrict__ seg_max,
+                              const float *__restrict__ seg_sum, const float *__restrict__ out_dot_g,
+                              const float *__restrict__ g, const uint32_t *__restrict__ row_idx,
+                              const uint32_t *__restrict__ off, const uint32_t *__restrict__ mirror_index,
+                              uint32_t n_rows, uint32_t F, uint32_t H, float slope) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t head_vecs = F / VEC / H;
+  const uint32_t n_edges = __ldg(off + n_rows);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kEdgeQuantum < n_edges; qw += nwarps) {
+    const uint32_t e0 = (uint32_t)(qw * kEdgeQuantum);
+    const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kEdgeQuantum);
+    for (uint32_t h = 0; h < H; h++) { // one head at a time: the per-row accumulator is a single register
+      uint32_t row = eo_find_row(off, n_rows, e0);
+      uint32_t row_end = __ldg(off + row + 1);
+      float d_acc = 0.f;
+      for (uint32_t e = e0; e < e1; e++) {
+        if (e >= row_end) {
+          if (lane == 0 && d_acc != 0.f)
+            atomicAdd(d_grad + (size_t)row * H + h, d_acc);
+          d_acc = 0.f;
+          do {
+            row++;
+            row_end = __ldg(off + row + 1);
+          } while (e >= row_end);
+        }
+        const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
+        const size_t rh = (size_t)row * H + h;
+        const float pre = __ldg(s_att + (size_t)slot * H + h) + __ldg(d_att + rh);
+        const float a = expf(leaky(pre, slope) - __ldg(seg_max + rh)) / __ldg(seg_sum + rh);
+        const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F) + h * head_vecs;
+        const V *mm = reinterpret_cast<const V *>(mirror + (size_t)slot * F) + h * head_vecs;
+        V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F) + h * head_vecs;
+        float dot = 0.f;
+        for (uint32_t c = lane; c < head_vecs; c += 32) {
+          V gv = __ldg(gm + c);
+          dot += vec_dot(__ldg(mm + c), gv);
+          vec_red_add<VEC>(dm + c, vec_scale(gv, a));
+        }
+        dot = warp_sum(dot);
+        const float d_pre = a * (dot - __ldg(out_dot_g + rh)) * (pre > 0.f ? 1.f : slope);
+        if (lane == 0)
+          atomicAdd(s_grad + (size_t)slot * H + h, d_pre);
+        d_acc += d_pre;
+      }
+      if (lane == 0 && d_acc != 0.f)
+        atomicAdd(d_grad + (size_t)row * H + h, d_acc);
+    }
+  } // quantum loop
+}
+
 // ---- (vid,row) records read from mapped pinned host memory ---------------------------------------------------
 template <bool ACCUM>
 __global__ void __launch_bounds__(kThreads)
@@ -542,6 +656,55 @@ int nts_aggregate_dst_fuse_weight_backward(float *mirror_grad, float *edge_weigh
   return nts_aggregate_dst_fuse_weight_backward_heads(mirror_grad, edge_weight_grad, mirror, edge_weight, dst_grad,
                                                       row_indices, column_offset, mirror_index, batch_size,
                                                       feature_size, 1, stream);
+}
+
+int nts_gat_softmax_stats(float *seg_max, float *seg_sum, const float *src_score, const float *dst_score,
+                          const nts_vid_t *row_indices, const nts_vid_t *column_offset, const nts_vid_t *mirror_index,
+                          nts_vid_t batch_size, nts_vid_t heads, float negative_slope, void *stream) {
+  if (batch_size == 0 || heads == 0)
+    return 0;
+  NTS_ARG_CHECK(seg_max && seg_sum && src_score && dst_score && row_indices && column_offset && mirror_index,
+                "null pointer passed to gat_softmax_stats");
+  unsigned grid = (batch_size + kRowsPerCta - 1) / kRowsPerCta;
+  gat_softmax_stats_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(seg_max, seg_sum, src_score, dst_score,
+                                                                     row_indices, column_offset, mirror_index,
+                                                                     batch_size, heads, negative_slope);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_gat_fused_aggregate_backward(float *mirror_grad, float *src_score_grad, float *dst_score_grad,
+                                     const float *mirror, const float *src_score, const float *dst_score,
+                                     const float *seg_max, const float *seg_sum, const float *out_dot_grad,
+                                     const float *dst_grad, const nts_vid_t *row_indices,
+                                     const nts_vid_t *column_offset, const nts_vid_t *mirror_index,
+                                     nts_vid_t batch_size, nts_vid_t feature_size, nts_vid_t heads,
+                                     float negative_slope, void *stream) {
+  cudaStream_t st = as_stream(stream);
+  if (batch_size == 0 || feature_size == 0)
+    return 0;
+  NTS_ARG_CHECK(mirror_grad && src_score_grad && dst_score_grad && mirror && src_score && dst_score && seg_max &&
+                    seg_sum && out_dot_grad && dst_grad && row_indices && column_offset && mirror_index,
+                "null pointer passed to fused GAT backward");
+  NTS_ARG_CHECK(heads >= 1 && feature_size % heads == 0, "feature_size must be a multiple of heads");
+  int vec = pick_vec(feature_size, mirror_grad, mirror, dst_grad);
+  while (vec > 1 && (feature_size / heads) % vec != 0)
+    vec >>= 1;
+  unsigned grid = full_grid();
+#define NTS_GATB(V_)                                                                                           \
+  gat_fused_backward_kernel<V_><<<grid, kThreads, 0, st>>>(mirror_grad, src_score_grad, dst_score_grad, mirror, \
+                                                           src_score, dst_score, seg_max, seg_sum, out_dot_grad, \
+                                                           dst_grad, row_indices, column_offset, mirror_index,  \
+                                                           batch_size, feature_size, heads, negative_slope)
+  if (vec == 4)
+    NTS_GATB(4);
+  else if (vec == 2)
+    NTS_GATB(2);
+  else
+    NTS_GATB(1);
+#undef NTS_GATB
+  NTS_LAUNCH_CHECK();
+  return 0;
 }
 
 int nts_deserialize_records(float *mirror, const float *records, nts_vid_t n_records, nts_vid_t feature_size,

@@ -302,3 +302,54 @@ class DistGPUAggregateDstFuseWeight(_EdgeOp):
 
     def get_additional_grad(self):
         return self.e_weight_grad
+
+
+class DistGPUFusedGATOp(_EdgeOp):
+    """K7: the whole attention + aggregation of one GAT layer in two kernels forward and one backward, never
+    materialising an edge-sized tensor (toolkits/GAT_CPU_DIST_OPTM.hpp:196-241 keeps [E,1] logits / attention;
+    toolkits/GAT_GPU_DIST.hpp:187-219 keeps four [E,F] messages).
+
+        forward(mirror [M, H*D], src_score [M, H], dst_score [V, H]) -> out [V, H*D]
+            a[e,h] = softmax over the in-edges of dst(e) of leaky_relu(src_score[slot(e),h] + dst_score[dst(e),h])
+            out[d, hD:(h+1)D] = sum_e a[e,h] * mirror[slot(e), hD:(h+1)D]
+        backward(grad_out) -> (d_mirror, d_src_score, d_dst_score)
+    """
+
+    def __init__(self, partitioned_graph, active=None, negative_slope=0.2):
+        super().__init__(partitioned_graph, active)
+        self.slope = float(negative_slope)
+        self._saved = None
+
+    def forward(self, mirror, src_score, dst_score):
+        pg = self._topo()
+        x = _check_input(mirror, "mirror")
+        s = _check_input(src_score, "src_score")
+        d = _check_input(dst_score, "dst_score")
+        H = int(s.shape[1])
+        seg_max = torch.empty((pg.owned_vertices, H), dtype=torch.float32, device=x.device)
+        seg_sum = torch.empty_like(seg_max)
+        _lib.call("nts_gat_softmax_stats", _ptr(seg_max), _ptr(seg_sum), _ptr(s), _ptr(d), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, H, self.slope, _stream())
+        out = torch.zeros((pg.owned_vertices, x.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.call("nts_gat_fused_aggregate_forward", _ptr(x), _ptr(out), _ptr(s), _ptr(d), _ptr(seg_max),
+                  _ptr(seg_sum), _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu),
+                  pg.owned_vertices, pg.owned_edges, x.shape[1], H, self.slope, _stream())
+        self._saved = (x, s, d, seg_max, seg_sum, out)
+        return out
+
+    def backward(self, f_output_grad):
+        pg = self._topo()
+        g = _check_input(f_output_grad, "output_grad")
+        x, s, d, seg_max, seg_sum, out = self._saved
+        H = int(s.shape[1])
+        D = x.shape[1] // H
+        # sum_e a[e,h] * <mirror[slot(e),h], g[d,h]> == <out[d,h], g[d,h]>: the softmax backward needs no edge pass
+        out_dot_g = (out.detach() * g).view(-1, H, D).sum(-1).contiguous()
+        dm = torch.zeros_like(x)
+        ds = torch.zeros_like(s)
+        dd = torch.zeros_like(d)
+        _lib.call("nts_gat_fused_aggregate_backward", _ptr(dm), _ptr(ds), _ptr(dd), _ptr(x), _ptr(s), _ptr(d),
+                  _ptr(seg_max), _ptr(seg_sum), _ptr(out_dot_g), _ptr(g), _ptr(pg.row_indices_gpu),
+                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, x.shape[1], H,
+                  self.slope, _stream())
+        return dm, ds, dd

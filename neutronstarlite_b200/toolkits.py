@@ -168,8 +168,9 @@ class GATImpl:
     message; the only edge-sized tensors are [E, H]."""
 
     def __init__(self, partitioned_graph, layers, features, labels, mask, heads=8, learn_rate=0.01,
-                 weight_decay=0.0001, exchange=None, seed=0, sum_fanout_grads=True):
+                 weight_decay=0.0001, exchange=None, seed=0, sum_fanout_grads=True, fused_kernel=False):
         self.pg = partitioned_graph
+        self.fused_kernel = fused_kernel  # True: K7 (ops.DistGPUFusedGATOp), no edge-sized tensors at all
         self.layers = list(layers)
         self.device = features.device
         self.heads = [heads] * (len(self.layers) - 2) + [1]
@@ -213,12 +214,15 @@ class GATImpl:
                 lambda m, _i=i: (m.view(-1, H, D) * self.al[_i].W).sum(-1).contiguous(), mirror)
             dst_att = ctx.runVertexForward(
                 lambda x, _i=i: (x.view(-1, H, D) * self.ar[_i].W).sum(-1).contiguous(), X_trans)
-            e_src = ctx.runGraphOp(ops.DistGPUScatterSrc, pg, None, src_att)
-            e_dst = ctx.runGraphOp(ops.DistGPUScatterDst, pg, None, dst_att)
-            e_msg = e_src + e_dst  # (the reference concatenates the two [E,1] columns and sums them, :218-224)
-            m = ctx.runEdgeForward(lambda t: torch.nn.functional.leaky_relu(t, 0.2), e_msg)
-            a = ctx.runGraphOp(ops.DistGPUEdgeSoftMax, pg, None, m)
-            nbr = ctx.runGraphOp(ops.DistGPUAggregateDstFuseWeight, pg, None, mirror, a)
+            if self.fused_kernel:
+                nbr = ctx.runGraphOpN(ops.DistGPUFusedGATOp, pg, None, [mirror, src_att, dst_att])
+            else:
+                e_src = ctx.runGraphOp(ops.DistGPUScatterSrc, pg, None, src_att)
+                e_dst = ctx.runGraphOp(ops.DistGPUScatterDst, pg, None, dst_att)
+                e_msg = e_src + e_dst  # (the reference concatenates the two [E,1] columns and sums them, :218-224)
+                m = ctx.runEdgeForward(lambda t: torch.nn.functional.leaky_relu(t, 0.2), e_msg)
+                a = ctx.runGraphOp(ops.DistGPUEdgeSoftMax, pg, None, m)
+                nbr = ctx.runGraphOp(ops.DistGPUAggregateDstFuseWeight, pg, None, mirror, a)
             if last:
                 self.X[i + 1] = ctx.runVertexForward(lambda t: t.log_softmax(1), nbr)
             else:

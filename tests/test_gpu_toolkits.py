@@ -91,8 +91,9 @@ def torch_gat_reference(pg, layers, heads, feats, labels, mask, Ws, als, ars):
     return torch.nn.functional.nll_loss(x[tr], labels[tr])
 
 
+@pytest.mark.parametrize("fused_kernel", [False, True])
 @pytest.mark.parametrize("heads", [1, 4])
-def test_gat_epoch_matches_torch_autograd(heads):
+def test_gat_epoch_matches_torch_autograd(heads, fused_kernel):
     from neutronstarlite_b200.graph import HostGraph, PartitionedGraph
     from neutronstarlite_b200.toolkits import GATImpl
     d = dev()
@@ -103,7 +104,8 @@ def test_gat_epoch_matches_torch_autograd(heads):
     feats = (torch.rand((V, layers[0]), generator=gen) * 2 - 1).to(d)
     labels = torch.randint(0, layers[-1], (V,), generator=gen).to(d)
     mask = (torch.arange(V) % 3).to(d)
-    model = GATImpl(pg, layers, feats.clone(), labels, mask, heads=heads, sum_fanout_grads=True)
+    model = GATImpl(pg, layers, feats.clone(), labels, mask, heads=heads, sum_fanout_grads=True,
+                    fused_kernel=fused_kernel)
     clone = lambda ps: [p.W.detach().clone().requires_grad_(True) for p in ps]
     Ws, als, ars = clone(model.P), clone(model.al), clone(model.ar)
     ref_loss = torch_gat_reference(pg, layers, model.heads, feats, labels, mask, Ws, als, ars)

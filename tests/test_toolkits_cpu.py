@@ -90,6 +90,27 @@ def fake_ops(monkeypatch):
         self._dw = (self._m[G.slot].view(-1, H, D) * gd).sum(-1)
         return torch.zeros(G.M, H, D).index_add_(0, G.slot, gd * self._aw[:, :, None]).reshape(G.M, H * D)
     patch(ops.DistGPUAggregateDstFuseWeight, fw_fwd, fw_bwd, lambda self: self._dw)
+
+    # K7 stand-in: same contract as ops.DistGPUFusedGATOp, gradients from a local autograd graph
+    def fg_fwd(self, mirror, s, d):
+        with torch.enable_grad():
+            m_, s_, d_ = (t.detach().clone().requires_grad_(True) for t in (mirror, s, d))
+            H = s.shape[1]
+            D = mirror.shape[1] // H
+            lg = torch.nn.functional.leaky_relu(s_[G.slot] + d_[G.dst], 0.2)
+            mx = torch.full((G.V, H), -float("inf")).scatter_reduce(0, G.dst[:, None].expand(-1, H), lg.detach(), "amax")
+            ex = torch.exp(lg - mx[G.dst])
+            a = ex / torch.zeros(G.V, H).index_add_(0, G.dst, ex)[G.dst]
+            out = torch.zeros(G.V, H, D).index_add_(0, G.dst, m_[G.slot].view(-1, H, D) * a[:, :, None]).reshape(G.V, H * D)
+        self._g = (m_, s_, d_, out)
+        return out.detach()
+
+    def fg_bwd(self, g):
+        m_, s_, d_, out = self._g
+        return torch.autograd.grad(out, (m_, s_, d_), g.detach())
+    monkeypatch.setattr(ops.DistGPUFusedGATOp, "__init__", lambda self, pg, active=None, **kw: None)
+    monkeypatch.setattr(ops.DistGPUFusedGATOp, "forward", fg_fwd)
+    monkeypatch.setattr(ops.DistGPUFusedGATOp, "backward", fg_bwd)
     return G
 
 
@@ -145,13 +166,15 @@ def test_gcn_tape_matches_autograd(fake_ops):
     assert torch.isfinite(loss2)
 
 
+@pytest.mark.parametrize("fused_kernel", [False, True])
 @pytest.mark.parametrize("heads", [1, 4])
-def test_gat_tape_matches_autograd(fake_ops, heads):
+def test_gat_tape_matches_autograd(fake_ops, heads, fused_kernel):
     from neutronstarlite_b200.toolkits import GATImpl
     G = fake_ops
     layers = [13, 16, 8, 5]
     feats, labels, mask = _data(G.V, layers[0], layers[-1])
-    model = GATImpl(G.pg, layers, feats.clone(), labels, mask, heads=heads, exchange=object(), sum_fanout_grads=True)
+    model = GATImpl(G.pg, layers, feats.clone(), labels, mask, heads=heads, exchange=object(), sum_fanout_grads=True,
+                    fused_kernel=fused_kernel)
     clone = lambda ps: [p.W.detach().clone().requires_grad_(True) for p in ps]
     Ws, als, ars = clone(model.P), clone(model.al), clone(model.ar)
     ref = _ref_gat(G, layers, model.heads, feats, labels, mask, Ws, als, ars)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--layers", default="602-64-64-41")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--fused-kernel", type=int, default=1, help="1: K7 DistGPUFusedGATOp, 0: [E,H] operator chain")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     V, E_rand, _ = synth.WORKLOADS[a.workload]
@@ -45,7 +46,8 @@ def main():
     del src, dst, has_src
     torch.cuda.empty_cache()
     feats, labels, mask = synth.features_labels_mask(V, layers[0], layers[-1], dev)
-    model = GATImpl(pg, layers, feats, labels, mask, heads=a.heads, exchange=GpuExchange(pg))
+    model = GATImpl(pg, layers, feats, labels, mask, heads=a.heads, exchange=GpuExchange(pg),
+                    fused_kernel=bool(a.fused_kernel))
     for _ in range(a.warmup):
         model.run_epoch()
     torch.cuda.synchronize()
@@ -59,8 +61,9 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     n_layers = len(layers) - 1
     print(json.dumps({
-        "workload": "%s-shaped, %d V, %d E, %d-layer GAT %s, %d heads (hidden layers), fused aggregation path" % (
-            a.workload, V, E, n_layers, a.layers, a.heads),
+        "workload": "%s-shaped, %d V, %d E, %d-layer GAT %s, %d heads (hidden layers), %s" % (
+            a.workload, V, E, n_layers, a.layers, a.heads,
+            "K7 fully fused attention+aggregation" if a.fused_kernel else "[E,H] operator chain + fused aggregation"),
         "ms_per_epoch": ms, "epochs_per_sec": 1e3 / ms,
         "aggregated_edges_per_sec": 2 * n_layers * E / (ms * 1e-3),
         "loss": float(loss.item()), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,

@@ -1,0 +1,52 @@
+#!/usr/bin/env python3
+"""Small driver for `compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitizer_smoke.py`:
+every kernel family of libnts_b200 once on small inputs (both aggregation variants, odd widths, hubs, empty rows)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from neutronstarlite_b200 import _lib, ops
+from neutronstarlite_b200.exchange import GpuExchange
+from neutronstarlite_b200.graph import HostGraph, PartitionedGraph
+
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(0)
+V, E = 700, 9000
+edges = np.stack([rng.integers(0, V, E), rng.integers(0, V, E)], 1).astype(np.uint32)
+edges[:1500, 1] = 3
+pg = PartitionedGraph(HostGraph(edges, V), 1, 0).generate_all(device=dev, dist=True)
+for variant in (1, 2):
+    _lib.call("nts_aggregate_set_variant", variant, 0)
+    for F in (602, 128, 41, 7, 172):
+        x = torch.rand((V, F), device=dev)
+        op = ops.ForwardSingleGPUfuseOp(pg)
+        y = op.forward(x)
+        dx = op.backward(y)
+_lib.call("nts_aggregate_set_variant", 0, 0)
+ex = GpuExchange(pg)
+dep = ops.DistGPUGetDepNbrOp(pg, None, exchange=ex)
+for H, D in ((1, 16), (4, 8)):
+    x = torch.rand((V, H * D), device=dev)
+    mirror = dep.forward(x)
+    e_src = ops.DistGPUScatterSrc(pg).forward(mirror[:, :H].contiguous())
+    e_dst = ops.DistGPUScatterDst(pg).forward(x[:, :H].contiguous())
+    sm = ops.DistGPUEdgeSoftMax(pg)
+    a = sm.forward(e_src + e_dst)
+    fw = ops.DistGPUAggregateDstFuseWeight(pg)
+    y = fw.forward(mirror, a)
+    dm = fw.backward(y)
+    da = fw.get_additional_grad()
+    g_in = sm.backward(da)
+    ops.DistGPUScatterSrc(pg).backward(g_in)
+    ops.DistGPUScatterDst(pg).backward(g_in)
+    ops.DistGPUAggregateDst(pg).forward(torch.rand((pg.owned_edges, D), device=dev))
+    dep.backward(dm)
+    fused = ops.DistGPUFusedGATOp(pg)
+    out = fused.forward(mirror, mirror[:, :H].contiguous(), x[:, :H].contiguous())
+    fused.backward(out)
+torch.cuda.synchronize()
+print("sanitizer smoke done, launches:", _lib.load().nts_kernel_launch_count())
