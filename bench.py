@@ -150,6 +150,47 @@ def reference_cpu_epochs(V, layers, edges_u32, steps, warmup, threads=None):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def reference_cpu_op_level(V, layers, edges_u32, threads=None):
+    """Op-level CPU numbers (BASELINE.md plan 3a): ForwardCPUfuseOp::forward / backward of the unmodified reference,
+    bracketed with its own get_time() by oracle/_ref/nts_ref_driver in `time` mode, one warm call + 1 timed call per
+    width.  Returns {"F602": {"forward_s":..., "backward_s":..., "gedges_per_s_fwd":...}, ...} or None."""
+    import numpy as np
+    binary = os.path.join(ROOT, "oracle", "_ref", "nts_ref_driver")
+    if not os.path.exists(binary):
+        return None
+    cores = threads or os.cpu_count()
+    work = tempfile.mkdtemp(prefix="nts_bench_refop_")
+    out = {}
+    try:
+        efile = os.path.join(work, "g.edge")
+        edges_u32.astype(np.uint32).tofile(efile)
+        cfg = os.path.join(work, "g.cfg")
+        with open(cfg, "w") as f:
+            f.write("ALGORITHM:GCNCPU\nVERTICES:%d\nLAYERS:%s\nEPOCHS:1\nEDGE_FILE:%s\nFEATURE_FILE:random\n"
+                    "LABEL_FILE:random\nMASK_FILE:random\nPROC_OVERLAP:0\nPROC_LOCAL:0\nPROC_CUDA:0\nPROC_REP:0\n"
+                    "LOCK_FREE:1\nLEARN_RATE:0.01\nWEIGHT_DECAY:0.0001\nDECAY_RATE:0.97\nDECAY_EPOCH:100\n"
+                    "DROP_RATE:0.0\n" % (V, "-".join(str(x) for x in layers), efile))
+        env = dict(os.environ)
+        env["NTS_THREADS"] = str(cores)
+        env["OMP_NUM_THREADS"] = str(cores)
+        for F in layers[:-1]:
+            try:
+                p = subprocess.run([binary, cfg, work, "time", str(F), "1"], stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL, text=True, env=env, timeout=600)
+                line = [ln for ln in p.stdout.splitlines() if ln.startswith("{\"ref_cpu\"")]
+                if line:
+                    r = json.loads(line[-1])
+                    E = int(edges_u32.shape[0])
+                    out["F%d" % F] = {"forward_s": r["forward_s"], "backward_s": r["backward_s"],
+                                      "gedges_per_s_forward": E / r["forward_s"] / 1e9, "threads": r["threads"]}
+            except Exception:
+                pass
+        return out or None
+    finally:
+        import shutil
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores):
     """Fallback when the reference binary is absent: the plain-C port of the aggregation loops (oracle/nts_oracle.c),
     aggregation calls only (fwd F0, fwd F1, bwd F1)."""
@@ -389,7 +430,7 @@ def main():
             edges = _sample_edges_cpu(V, E_rand, div)
             r = reference_cpu_epochs(V, layers, edges, 2, 1)
             cpu = {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
-                   "s_per_epoch": r["s_per_epoch"],
+                   "s_per_epoch": r["s_per_epoch"], "op_level": reference_cpu_op_level(V, layers, edges),
                    "sample": "first 1/%d of the workload's random edges + all self loops (%d edges), all V, full "
                              "widths; unmodified reference ALGORITHM:GCNCPU, 1 warm-up + 2 timed epochs" % (
                                  div, edges.shape[0])}

@@ -408,3 +408,41 @@ def test_multi_head_fused_aggregation(H, D):
         dw_ref[:, h:h + 1] = dwh
     close(dm, dm_ref)
     close(dw, dw_ref)
+
+
+def test_offsets_beyond_32_bits():
+    """Rows whose element offset exceeds 2^32 (the reference kernels compute feature_size*batch_size in 32 bits,
+    cuda/ntsCUDAFuseKernel.cuh:280,299, and wrap): 9.0 M source rows x 512 floats = 4.6e9 elements (18.4 GB)."""
+    d = dev()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30e9:
+        pytest.skip("needs ~20 GB of free device memory")
+    V_src, F, n_rows = 9_000_000, 512, 257
+    x = torch.zeros((V_src, F), dtype=torch.float32, device=d)
+    rng = np.random.default_rng(11)
+    # sources concentrated at both ends of the matrix, in particular beyond element 2^32 (row 8 388 608)
+    picks = np.concatenate([rng.integers(0, 1000, 2000), rng.integers(V_src - 1000, V_src, 6000),
+                            rng.integers(8_388_608, 8_389_608, 2000)]).astype(np.uint32)
+    rng.shuffle(picks)
+    uniq = np.unique(picks)
+    vals = rng.uniform(-1, 1, (uniq.shape[0], F)).astype(np.float32)
+    x[torch.from_numpy(uniq.astype(np.int64)).to(d)] = torch.from_numpy(vals).to(d)
+    deg = rng.integers(0, 80, n_rows)
+    deg[5] = 3000  # one long row
+    off = np.zeros(n_rows + 1, dtype=np.uint32)
+    np.cumsum(deg, out=off[1:])
+    E = int(off[-1])
+    idx = np.resize(picks, E).astype(np.uint32)
+    w = rng.uniform(-1, 1, E).astype(np.float32)
+    out = torch.zeros((n_rows, F), dtype=torch.float32, device=d)
+    L = lib()
+    d_off, d_idx, d_w = up_u32(off), up_u32(idx), up(w)
+    L.call("nts_segment_gather_sum", x.data_ptr(), out.data_ptr(), d_w.data_ptr(), d_idx.data_ptr(), d_off.data_ptr(),
+           0, n_rows, E, F, stream())
+    torch.cuda.synchronize()
+    # oracle on the compacted matrix
+    pos = np.searchsorted(uniq, idx).astype(np.uint32)
+    ref = oracle_c.segment_gather_sum(off, pos, w, vals)
+    close(out.cpu().numpy(), ref)
+    del x
+    torch.cuda.empty_cache()
