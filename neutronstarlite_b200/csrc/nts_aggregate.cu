@@ -137,15 +137,19 @@ __device__ __forceinline__ float att_weight(float s, float d, float m, float inv
 // U    : edges loaded before the FMAs start (memory-level parallelism = U*K loads per lane)
 // BULK : stage index/weight tiles with cp.async.bulk + mbarrier (variant 2)
 // MINB : minimum resident CTAs per SM handed to __launch_bounds__ (register cap = 65536 / (256*MINB))
-// ATT  : weights are recomputed from attention scores (AttParams) instead of loaded (fused GAT, K7)
-template <int VEC, int K, int U, bool BULK, int MINB = 1, bool ATT = false>
+// HM   : head mode.  0 = one weight per edge (or none);
+//                    1 = multi-head weights w[E, H]: every lane scales its columns with the weight of the head
+//                        that owns them (head of column c = c / D), loaded per lane (lanes of one head broadcast);
+//                    2 = fused GAT attention: the weight is recomputed from per-vertex scores (AttParams).
+//        For HM != 0 a lane's K chunks may belong to different heads, so weights / row constants are per chunk.
+template <int VEC, int K, int U, bool BULK, int MINB = 1, int HM = 0>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     segment_gather_sum_kernel(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ w,
                               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
                               const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
                               uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
-                              uint32_t tile_major, uint32_t w_stride, AttParams att) {
-  static_assert(!(ATT && BULK), "attention weights are not bulk-staged");
+                              uint32_t tile_major, uint32_t heads, AttParams att) {
+  static_assert(!(HM != 0 && BULK), "per-head weights are not bulk-staged");
   using V = typename Vec<VEC>::type;
   const uint32_t n_edges = (uint32_t)n_edges64;
   const uint32_t lane = threadIdx.x & 31;
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     if (ce1 > n_edges)
       ce1 = n_edges;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    const uint32_t span_cap = (kWarpsPerBlock / 1) * Q + 8; // elements reserved per array (host sizes smem to this)
+    const uint32_t span_cap = kWarpsPerBlock * Q + 8; // elements reserved per array (host sizes smem to this)
     s_idx = reinterpret_cast<uint32_t *>(smem_raw + 16);
     s_w = reinterpret_cast<float *>(smem_raw + 16 + (size_t)span_cap * 4);
     if (ce0 < ce1) {
@@ -216,9 +220,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   // column tile handled by this warp
   const uint32_t c0 = tile * tile_vecs + lane; // first vector column of this lane
   bool act[K];
+  uint32_t hk[K]; // head that owns chunk k of this lane (HM != 0)
 #pragma unroll
-  for (int k = 0; k < K; k++)
+  for (int k = 0; k < K; k++) {
     act[k] = (k * 32 + lane) < tile_vecs && (c0 + k * 32) < nvec;
+    hk[k] = 0;
+    if constexpr (HM != 0)
+      hk[k] = act[k] ? ((c0 + k * 32) * VEC) / (F / heads) : 0u;
+  }
 
   // first row of the quantum (overlaps with the bulk copy in flight)
   uint32_t row = find_row(off, n_rows, e0);
@@ -230,14 +239,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   for (int k = 0; k < K; k++)
     zero_vec(acc[k]);
 
-  // per-row attention constants of head `tile` (ATT only)
-  float att_d = 0.f, att_m = 0.f, att_iz = 0.f;
+  // per-row attention constants of the heads of this lane's chunks (HM == 2)
+  float att_d[K], att_m[K], att_iz[K];
   auto load_att_row = [&]() {
-    if constexpr (ATT) {
-      const size_t o = (size_t)row * w_stride + tile;
-      att_d = __ldg(att.d + o);
-      att_m = __ldg(att.m + o);
-      att_iz = 1.f / __ldg(att.z + o);
+    if constexpr (HM == 2) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const size_t o = (size_t)row * heads + hk[k];
+        att_d[k] = __ldg(att.d + o);
+        att_m[k] = __ldg(att.m + o);
+        att_iz[k] = 1.f / __ldg(att.z + o);
+      }
     }
   };
   load_att_row();
@@ -265,6 +277,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     row_started_inside = true;
     load_att_row();
   };
+  // weight of (edge value, chunk k) in the accumulate phase
+  auto weight_of = [&](float raw, int k) -> float {
+    if constexpr (HM == 2)
+      return att_weight(raw, att_d[k], att_m[k], att_iz[k], att.slope);
+    else
+      return raw;
+  };
 
   if constexpr (BULK) {
     if (bulk_bytes)
@@ -279,72 +298,81 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
       if (lane < cnt) {
         uint32_t id = __ldg(idx + e + lane);
         my_src = slot_of ? __ldg(slot_of + id) : id - base;
-        if constexpr (ATT)
-          my_w = __ldg(att.s + (size_t)my_src * w_stride + tile); // source score of this edge for head `tile`
-        else if (w) // multi-head weights [E, H]: column tile t is head t (w_stride = H), else one weight per edge
-          my_w = __ldg(w + (size_t)(e + lane) * w_stride + (w_stride > 1 ? tile : 0u));
+        if constexpr (HM == 0)
+          if (w)
+            my_w = __ldg(w + e + lane);
       }
     }
     uint32_t j = 0;
     // full groups of U edges: U*K independent vector loads per lane, then the FMAs
     for (; j + U <= cnt; j += U) {
       V v[U][K];
-      float wu[U];
+      float wu[U][HM == 0 ? 1 : K];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         uint32_t s;
         if constexpr (BULK) {
           uint32_t id = s_idx[e + j + u - cta_e_base];
           s = slot_of ? __ldg(slot_of + id) : id - base;
-          wu[u] = w ? s_w[e + j + u - cta_e_base] : 1.f;
+          wu[u][0] = w ? s_w[e + j + u - cta_e_base] : 1.f;
         } else {
           s = __shfl_sync(0xffffffffu, my_src, j + u);
-          wu[u] = __shfl_sync(0xffffffffu, my_w, j + u);
+          if constexpr (HM == 0)
+            wu[u][0] = __shfl_sync(0xffffffffu, my_w, j + u);
         }
         const V *p = reinterpret_cast<const V *>(in + (size_t)s * F) + c0;
 #pragma unroll
-        for (int k = 0; k < K; k++)
+        for (int k = 0; k < K; k++) {
           if (act[k])
             v[u][k] = ldg_vec<VEC>(p + k * 32);
+          if constexpr (HM == 1)
+            wu[u][k] = act[k] ? __ldg(w + (size_t)(e + j + u) * heads + hk[k]) : 0.f;
+          if constexpr (HM == 2)
+            wu[u][k] = act[k] ? __ldg(att.s + (size_t)s * heads + hk[k]) : 0.f;
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const uint32_t ee = e + j + u;
         if (ee >= row_end)
           advance(ee);
-        const float wq = ATT ? att_weight(wu[u], att_d, att_m, att_iz, att.slope) : wu[u];
 #pragma unroll
         for (int k = 0; k < K; k++)
           if (act[k])
-            fma_vec(acc[k], wq, v[u][k]);
+            fma_vec(acc[k], weight_of(wu[u][HM == 0 ? 0 : k], k), v[u][k]);
       }
     }
     // remainder (< U edges)
     for (; j < cnt; j++) {
       uint32_t s;
-      float wj;
+      float wj[HM == 0 ? 1 : K];
       if constexpr (BULK) {
         uint32_t id = s_idx[e + j - cta_e_base];
         s = slot_of ? __ldg(slot_of + id) : id - base;
-        wj = w ? s_w[e + j - cta_e_base] : 1.f;
+        wj[0] = w ? s_w[e + j - cta_e_base] : 1.f;
       } else {
         s = __shfl_sync(0xffffffffu, my_src, j);
-        wj = __shfl_sync(0xffffffffu, my_w, j);
+        if constexpr (HM == 0)
+          wj[0] = __shfl_sync(0xffffffffu, my_w, j);
       }
       const V *p = reinterpret_cast<const V *>(in + (size_t)s * F) + c0;
       V v1[K];
 #pragma unroll
-      for (int k = 0; k < K; k++)
+      for (int k = 0; k < K; k++) {
         if (act[k])
           v1[k] = ldg_vec<VEC>(p + k * 32);
+        if constexpr (HM == 1)
+          wj[k] = act[k] ? __ldg(w + (size_t)(e + j) * heads + hk[k]) : 0.f;
+        if constexpr (HM == 2)
+          wj[k] = act[k] ? __ldg(att.s + (size_t)s * heads + hk[k]) : 0.f;
+      }
       const uint32_t ee = e + j;
       if (ee >= row_end)
         advance(ee);
-      const float wq = ATT ? att_weight(wj, att_d, att_m, att_iz, att.slope) : wj;
 #pragma unroll
       for (int k = 0; k < K; k++)
         if (act[k])
-          fma_vec(acc[k], wq, v1[k]);
+          fma_vec(acc[k], weight_of(wj[HM == 0 ? 0 : k], k), v1[k]);
     }
   }
   // last row of the quantum: whole only if it started inside and also ends at/before e1
@@ -354,12 +382,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 // ---- host-side dispatch ---------------------------------------------------------------------------------
 struct LaunchShape {
   int vec, k, u, minb;
-  uint32_t tiles, tile_vecs, tile_major, w_stride;
+  uint32_t tiles, tile_vecs, tile_major, heads;
 };
 
 static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uint32_t heads) {
   LaunchShape s;
-  s.w_stride = 1;
+  s.heads = heads ? heads : 1;
   bool a16 = aligned_to(in, 16) && aligned_to(out, 16);
   bool a8 = aligned_to(in, 8) && aligned_to(out, 8);
   if (F % 4 == 0 && a16)
@@ -385,15 +413,8 @@ static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uin
     }
   }
   s.tile_vecs = (nvec + s.tiles - 1) / s.tiles;
-  if (heads > 1) { // one column tile per attention head: tile t covers columns [t*D, (t+1)*D)
-    s.tiles = heads;
-    s.tile_major = 0;
-    s.tile_vecs = nvec / heads;
-    s.w_stride = heads;
-  }
   s.k = (int)((s.tile_vecs + 31) / 32);
-  if (heads <= 1)
-    s.tiles = (nvec + s.tile_vecs - 1) / s.tile_vecs;
+  s.tiles = (nvec + s.tile_vecs - 1) / s.tile_vecs;
   // (U, min CTAs/SM): measured on B200 for the headline shapes (profiles/tune_r1_*.jsonl), generic rule otherwise
   s.minb = 1;
   int budget = 40 / (s.k * s.vec);
@@ -432,16 +453,21 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
   NTS_ARG_CHECK(blocks <= 0x7fffffffull, "aggregation grid too large");
   g_last_grid = (int)blocks;
   g_last_block = kWarpsPerBlock * 32;
-  if (att) {
-    if constexpr (MINB == 1) { // attention kernels exist for the untuned occupancy points only
+  if (att || sh.heads > 1) {
+    if constexpr (MINB == 1) { // per-head kernels exist for the untuned occupancy points only
       g_last_smem = 0;
-      segment_gather_sum_kernel<VEC, K, U, false, 1, true><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-          in, out, nullptr, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
-          sh.w_stride, *att);
+      if (att)
+        segment_gather_sum_kernel<VEC, K, U, false, 1, 2><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+            in, out, nullptr, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
+            sh.heads, *att);
+      else
+        segment_gather_sum_kernel<VEC, K, U, false, 1, 1><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
+            in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
+            sh.heads, kNoAtt);
       NTS_LAUNCH_CHECK();
       return 0;
     } else {
-      return fail(-1, "no attention kernel for this occupancy point", __FILE__, __LINE__);
+      return fail(-1, "no per-head kernel for this occupancy point", __FILE__, __LINE__);
     }
   }
   if (bulk) {
@@ -451,13 +477,12 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
     NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_last_smem = (int)smem;
     kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F,
-                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major, sh.w_stride,
-                                                              kNoAtt);
+                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major, 1u, kNoAtt);
   } else {
     g_last_smem = 0;
     segment_gather_sum_kernel<VEC, K, U, false, MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
-        in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
-        sh.w_stride, kNoAtt);
+        in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major, 1u,
+        kNoAtt);
   }
   NTS_LAUNCH_CHECK();
   return 0;
@@ -479,15 +504,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
     NTS_ARG_CHECK(F % heads == 0, "feature_size must be a multiple of heads");
   }
   LaunchShape s = pick_shape(in, out, F, heads);
-  if (att && heads == 1) { // single head: still one column tile per head so the per-row constants are per tile
-    s.tiles = 1;
-    s.tile_major = 0;
-    s.tile_vecs = F / s.vec;
-    s.k = (int)((s.tile_vecs + 31) / 32);
-    s.w_stride = 1;
-  }
-  if (heads > 1 || att) {
-    NTS_ARG_CHECK(s.k >= 1 && s.k <= 5, "head width too large for one column tile");
+  if (heads > 1 || att) { // per-head kernels: untuned occupancy point, shuffle-broadcast indices
     s.minb = 1;
     int budget = 40 / (s.k * s.vec);
     s.u = budget >= 8 ? 8 : (budget >= 4 ? 4 : 2);
