@@ -70,3 +70,36 @@ def test_partition_offsets_from_degrees_matches_reference(golden):
     g = golden
     raw = np.bincount(g.edges[:, 0], minlength=g.V)
     assert np.array_equal(partition_offsets_from_out_degree(raw, g.E, g.P), g.partition_offset)
+
+
+def test_host_builder_rejects_bad_input():
+    """Out-of-range vertex ids and bad ranks are reported through the status code (no silent clamping)."""
+    from neutronstarlite_b200 import _lib
+    L = _lib.load()
+    edges = np.array([[0, 1], [7, 2]], dtype=np.uint32)   # vertex 7 does not exist in a 5-vertex graph
+    out_d = np.zeros(5, dtype=np.uint32)
+    in_d = np.zeros(5, dtype=np.uint32)
+    assert L.nts_host_degrees(edges.ctypes.data, 2, 5, out_d.ctypes.data, in_d.ctypes.data) != 0
+    po = np.zeros(3, dtype=np.uint32)
+    assert L.nts_host_partition_offsets(edges.ctypes.data, 2, 5, 2, po.ctypes.data) != 0
+    ok = np.array([[0, 1], [4, 2]], dtype=np.uint32)
+    assert L.nts_host_partition_offsets(ok.ctypes.data, 2, 5, 0, po.ctypes.data) != 0      # zero partitions
+    counts = np.zeros(2, dtype=np.uint64)
+    po2 = np.array([0, 0, 5], dtype=np.uint32)
+    assert L.nts_host_chunk_edge_counts(ok.ctypes.data, 2, po2.ctypes.data, 2, 5, counts.ctypes.data) != 0  # bad rank
+
+
+def test_duplicates_and_self_loops_count_in_degrees():
+    """The reference counts duplicate edges and self loops in both degrees (data/cora.2708.edge.self has 302
+    duplicate pairs); weights follow from those counts."""
+    e = np.array([[0, 1], [0, 1], [1, 1], [2, 1], [2, 0]], dtype=np.uint32)
+    hg = HostGraph(e, 4)
+    out_d, in_d = hg.degrees()
+    assert out_d.tolist() == [2, 1, 2, 1] and in_d.tolist() == [1, 4, 1, 1]   # vertex 3 isolated -> clamped to 1
+    pg = PartitionedGraph(hg, 1, 0).generate_all()
+    c = pg.graph_chunks[0]
+    assert c.column_offset.tolist() == [0, 1, 5, 5, 5]
+    assert c.row_indices.tolist() == [2, 0, 0, 1, 2]
+    w = 1 / (np.sqrt(out_d[c.row_indices].astype(np.float64)).astype(np.float32) *
+             np.sqrt(in_d[[0, 1, 1, 1, 1]].astype(np.float64)).astype(np.float32))
+    assert np.array_equal(c.edge_weight_forward, w.astype(np.float32))
