@@ -233,6 +233,48 @@ int nts_ipc_close_handle(void *peer_ptr);
 int nts_signal_set(uint32_t *flag, uint32_t value, void *stream);
 int nts_signal_wait_geq(const uint32_t *flag, uint32_t value, void *stream);
 
+/* ---- the exchange engine: data plane of the distributed fused aggregation (peer-memory transport) ---------------------
+ * Replaces Graph::sync_compute_decoupled / compute_sync_decoupled (core/graph.hpp:3455-3719) and the host-staged
+ * NtsGraphCommunicator (comm/network.cpp:159-844).  The caller owns the CONTROL plane: it builds the plan arrays
+ * (who needs which rows; neutronstarlite_b200/exchange.py::ExchangePlan documents them) and moves the two 64-byte IPC
+ * handles per rank between processes (torch.distributed here, MPI in the reference's host code); the engine owns
+ * windows, flags, streams, events and the launch sequence.  All pointers are device pointers that must outlive the
+ * engine; per-partition arrays have `partitions` entries (own entry ignored). */
+typedef struct nts_exchange nts_exchange;
+typedef struct nts_exchange_desc {
+  int partitions, rank;
+  nts_vid_t owned_vertices, dst_start;      /* V_p and partition_offset[rank] */
+  /* local chunk (sources in this partition): CSC + CSR of CSC_segment_pinned */
+  const nts_vid_t *local_column_offset, *local_row_indices, *local_row_offset, *local_column_indices;
+  const float *local_weight_forward, *local_weight_backward;
+  nts_vid_t local_edges;
+  /* all remote chunks merged: CSC whose indices are slots of the receive staging buffer ... */
+  const nts_vid_t *remote_column_offset, *remote_slots;
+  const float *remote_weight;
+  uint64_t remote_edges;
+  /* ... and compact CSR over the active sources (rows = send-staging layout) */
+  const nts_vid_t *backward_offsets, *backward_indices;
+  const float *backward_weight;
+  nts_vid_t recv_total, send_total;         /* rows I read from peers / rows peers read from me */
+  const nts_vid_t *need_count;              /* [P] rows of partition i that I read */
+  const nts_vid_t *const *need;             /* [P] device lists: local ids (within partition i) of those rows */
+  const nts_vid_t *send_count;              /* [P] rows of mine that peer j reads */
+  const nts_vid_t *send_rows_all;           /* device: concatenation over peers j != rank of those rows */
+  const nts_vid_t *peer_bwd_offset;         /* [P] row offset of MY slice inside peer j's backward window */
+} nts_exchange_desc;
+
+nts_exchange *nts_exchange_create(const nts_exchange_desc *desc);
+int nts_exchange_destroy(nts_exchange *ex);
+uint64_t nts_exchange_required_floats(const nts_exchange *ex, nts_vid_t feature_size);
+/* grow the exported window; *reallocated = 1 means: exchange handles again and call nts_exchange_open_peers */
+int nts_exchange_reserve(nts_exchange *ex, uint64_t floats, int *reallocated);
+int nts_exchange_handles(nts_exchange *ex, unsigned char window_handle[64], unsigned char flags_handle[64]);
+int nts_exchange_open_peers(nts_exchange *ex, const unsigned char *window_handles, const unsigned char *flag_handles);
+/* Y_p += sum_i A_{p<-i} X_i  (ForwardGPUfuseOp::forward, core/ntsDistGPUFusedGraphOp.hpp:56-73); y zeroed by caller */
+int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t feature_size, void *stream);
+/* dX_p += sum_j A_{j<-p}^T dY_j (ForwardGPUfuseOp::backward, :75-90); dx zeroed by caller */
+int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t feature_size, void *stream);
+
 /* ---- host-side graph preparation (C++ with OpenMP; no device involved) -----------------------------------
  * Restates the layout contract of core/graph.hpp:1185-1211 (partitioner), :4396-4401 (degree clamp),
  * core/ntsBaseOp.hpp:194-197 (edge weight) and core/PartitionedGraph.hpp:324-420 (per-source-partition chunks). */

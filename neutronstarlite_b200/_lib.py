@@ -82,6 +82,34 @@ SIGNATURES = {
     "nts_host_mirror_index": (_int, [_vp, _u64, _u32, _vp, _int, _vp, _vp]),
 }
 
+
+
+class ExchangeDesc(C.Structure):
+    """nts_exchange_desc of include/nts_b200.h."""
+    _fields_ = [
+        ("partitions", _int), ("rank", _int), ("owned_vertices", _u32), ("dst_start", _u32),
+        ("local_column_offset", _vp), ("local_row_indices", _vp), ("local_row_offset", _vp),
+        ("local_column_indices", _vp), ("local_weight_forward", _vp), ("local_weight_backward", _vp),
+        ("local_edges", _u32),
+        ("remote_column_offset", _vp), ("remote_slots", _vp), ("remote_weight", _vp), ("remote_edges", _u64),
+        ("backward_offsets", _vp), ("backward_indices", _vp), ("backward_weight", _vp),
+        ("recv_total", _u32), ("send_total", _u32),
+        ("need_count", C.POINTER(_u32)), ("need", C.POINTER(_vp)), ("send_count", C.POINTER(_u32)),
+        ("send_rows_all", _vp), ("peer_bwd_offset", C.POINTER(_u32)),
+    ]
+
+
+SIGNATURES.update({
+    "nts_exchange_create": (_vp, [C.POINTER(ExchangeDesc)]),
+    "nts_exchange_destroy": (_int, [_vp]),
+    "nts_exchange_required_floats": (_u64, [_vp, _u32]),
+    "nts_exchange_reserve": (_int, [_vp, _u64, C.POINTER(_int)]),
+    "nts_exchange_handles": (_int, [_vp, C.c_char_p, C.c_char_p]),
+    "nts_exchange_open_peers": (_int, [_vp, C.c_char_p, C.c_char_p]),
+    "nts_exchange_forward": (_int, [_vp, _vp, _vp, _u32, _vp]),
+    "nts_exchange_backward": (_int, [_vp, _vp, _vp, _u32, _vp]),
+})
+
 _lib = None
 
 

@@ -323,190 +323,107 @@ class GpuExchange:
                       cur.cuda_stream)
         return dx
 
-    # ---- peer-memory transport ------------------------------------------------------------------------------------
+    # ---- peer-memory transport: the C++ engine (csrc/nts_exchange.cu) --------------------------------------------------
     def _forward_p2p(self, x, y):
-        pg, plan, P, p = self.pg, self.plan, self.P, self.p
-        F = x.shape[1]
-        w = self._p2p
-        cur = torch.cuda.current_stream()
-        # publish my rows: copy into the exported window (the op input is borrowed torch storage, not IPC memory)
-        w.reserve(pg.owned_vertices, plan.recv_total, F)
-        epoch = w.begin(cur)
-        _lib.call("nts_memcpy_d2d", w.window, x.data_ptr(), x.numel() * 4, cur.cuda_stream)
-        w.commit(epoch, cur)
-        ops.gather_by_dst_from_src(pg.graph_chunks[p], y, x)     # local chunk while peers publish
-        recv = self._buf("frecv", plan.recv_total, F)
-        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
-        ring = plan.ring()
-        # pull every peer's rows on the side stream (NVLink loads by the receiver) while the local chunk aggregates
-        self.comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self.comm_stream):
-            for i in ring:
-                n = plan.need_count[i]
-                if n:
-                    seg = recv[int(offs[i]):int(offs[i + 1])]
-                    w.wait_published(i, epoch, self.comm_stream)
-                    _lib.call("nts_gather_rows", _ptr(seg), w.peer_ptr(i), _ptr(plan.need[i]), n, F,
-                              self.comm_stream.cuda_stream)
-            w.signal_consumed(epoch, self.comm_stream)
-        recv.record_stream(self.comm_stream)
-        cur.wait_stream(self.comm_stream)
-        self._aggregate_remote(y, recv)
+        self._p2p.reserve(x.shape[1])
+        ev = ops._timer.bracket("fwd", x.shape[1], self.pg.owned_edges, self.pg.owned_vertices) if ops._timer else None
+        if ev:
+            ev[0].record()
+        _lib.call("nts_exchange_forward", self._p2p.handle, _ptr(x), _ptr(y), x.shape[1],
+                  torch.cuda.current_stream().cuda_stream)
+        if ev:
+            ev[1].record()
         return y
 
     def _backward_p2p(self, g, dx):
-        pg, plan, P, p = self.pg, self.plan, self.P, self.p
-        F = g.shape[1]
-        w = self._p2p
-        cur = torch.cuda.current_stream()
-        # my partials for every peer go into MY exported window; peers pull their slice and add it
-        offs = np.concatenate([[0], np.cumsum([plan.need_count[i] if i != p else 0 for i in range(P)])])
-        w.reserve(pg.owned_vertices, plan.recv_total, F)
-        epoch = w.begin(cur)                       # peers are done with what I published last time
-        win = w.window_rows(plan.recv_total, F)
-        win.zero_()
-        self._partial_remote(win, g)
-        w.commit(epoch, cur)
-        # every peer j computed a slice for me inside ITS window: copy it out of peer memory over NVLink on the side
-        # stream (overlaps the local chunk), then one scatter-add launch once the local chunk is done with dx
-        recv = self._buf("brecv", plan.send_total, F)
-        self.comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self.comm_stream):
-            pos = 0
-            for j in range(P):
-                n = plan.send_count[j]
-                if j == p or not n:
-                    continue
-                w.wait_published(j, epoch, self.comm_stream)
-                src = w.peer_ptr(j) + int(w.peer_bwd_offset[j]) * F * 4
-                _lib.call("nts_memcpy_d2d", _ptr(recv[pos:pos + n]), src, n * F * 4, self.comm_stream.cuda_stream)
-                pos += n
-            w.signal_consumed(epoch, self.comm_stream)
-        recv.record_stream(self.comm_stream)
-        ops.gather_by_src_from_dst(pg.graph_chunks[p], dx, g)
-        cur.wait_stream(self.comm_stream)
-        if plan.send_total:
-            _lib.call("nts_scatter_add_rows_atomic", _ptr(dx), _ptr(recv), _ptr(plan.send_rows_all), plan.send_total, F,
-                      cur.cuda_stream)
+        self._p2p.reserve(g.shape[1])
+        ev = ops._timer.bracket("bwd", g.shape[1], self.pg.owned_edges, self.pg.owned_vertices) if ops._timer else None
+        if ev:
+            ev[0].record()
+        _lib.call("nts_exchange_backward", self._p2p.handle, _ptr(g), _ptr(dx), g.shape[1],
+                  torch.cuda.current_stream().cuda_stream)
+        if ev:
+            ev[1].record()
         return dx
 
 
 class _PeerWindows:
-    """CUDA-IPC windows: one exported device buffer per rank (rows published per call) plus two uint32 flag arrays
-    (published[rank], consumed[rank][peer]) for cross-GPU ordering.  Control plane: torch.distributed
-    (all_gather_object of the 64-byte IPC handles)."""
+    """Control plane of the peer-memory transport: hands the plan arrays to the C++ engine and moves the IPC handles
+    between ranks with torch.distributed; the data plane (windows, flags, streams, launch sequence) is
+    `nts_exchange_*` in csrc/nts_exchange.cu."""
 
     def __init__(self, ex):
+        import ctypes as C
         self.ex = ex
         P, p = ex.P, ex.p
-        self.P, self.p = P, p
-        L = _lib.load()
         pg, plan = ex.pg, ex.plan
-        self.capacity_floats = 0
-        self.window = 0
-        self.flags = L.nts_malloc_device(4 * (1 + P))
-        if not self.flags:
-            raise _lib.NtsError("flag allocation failed: " + L.nts_last_error().decode())
-        _lib.call("nts_zero", self.flags, 4 * (1 + P), 0)
-        _lib.call("nts_device_synchronize")
-        self.epoch = 0
-        self._peers = None
-        # backward: where my slice starts inside peer j's window = offset of chunk p in j's remote-chunk order
-        mine = torch.tensor([plan.need_count[i] if i != p else 0 for i in range(P)], dtype=torch.int64)
+        L = _lib.load()
+        # backward: where my slice starts inside peer j's window = rows peer j computes for partitions before me
         allc = [None] * P
-        dist.all_gather_object(allc, mine.tolist(), group=ex.group)
-        self.peer_bwd_offset = [int(sum(allc[j][:p])) for j in range(P)]
-        self._handle_flags = self._export(self.flags)
+        dist.all_gather_object(allc, [plan.need_count[i] if i != p else 0 for i in range(P)], group=ex.group)
+        bwd_off = [int(sum(allc[j][:p])) for j in range(P)]
+        c = pg.graph_chunks[p]
+        u32 = C.c_uint32 * P
+        self._keep = {
+            "need_count": u32(*[plan.need_count[i] if i != p else 0 for i in range(P)]),
+            "send_count": u32(*[plan.send_count[j] if j != p else 0 for j in range(P)]),
+            "bwd_off": u32(*bwd_off),
+            "need": (C.c_void_p * P)(*[_ptr(plan.need[i]) if plan.need[i] is not None and plan.need[i].numel() else None
+                                       for i in range(P)]),
+        }
+        d = _lib.ExchangeDesc()
+        d.partitions, d.rank = P, p
+        d.owned_vertices, d.dst_start = pg.owned_vertices, c.dst_range[0]
+        d.local_column_offset, d.local_row_indices = _ptr(c.column_offset_gpu), _ptr(c.row_indices_gpu)
+        d.local_row_offset, d.local_column_indices = _ptr(c.row_offset_gpu), _ptr(c.column_indices_gpu)
+        d.local_weight_forward, d.local_weight_backward = _ptr(c.edge_weight_forward_gpu), _ptr(c.edge_weight_backward_gpu)
+        d.local_edges = c.edge_size
+        d.remote_column_offset, d.remote_slots = _ptr(plan.remote_col_offset), _ptr(plan.remote_slots)
+        d.remote_weight, d.remote_edges = _ptr(plan.remote_w), plan.remote_edges
+        d.backward_offsets, d.backward_indices = _ptr(plan.bwd_offsets), _ptr(plan.bwd_indices)
+        d.backward_weight = _ptr(plan.bwd_w)
+        d.recv_total, d.send_total = plan.recv_total, plan.send_total
+        d.need_count = self._keep["need_count"]
+        d.need = C.cast(self._keep["need"], C.POINTER(C.c_void_p))
+        d.send_count = self._keep["send_count"]
+        d.send_rows_all = _ptr(plan.send_rows_all)
+        d.peer_bwd_offset = self._keep["bwd_off"]
+        self.handle = L.nts_exchange_create(C.byref(d))
+        if not self.handle:
+            raise _lib.NtsError("nts_exchange_create failed: " + L.nts_last_error().decode())
         self._reserved = set()
 
-    def _export(self, ptr):
-        import ctypes
-        buf = ctypes.create_string_buffer(_lib.C.sizeof(_lib.C.c_char) * 64)
-        _lib.call("nts_ipc_get_handle", ptr, buf)
-        return bytes(buf.raw)
-
-    def _ensure(self, floats):
-        """(Re)allocate the exported window so it holds `floats` float32 and re-open every peer's window."""
-        L = _lib.load()
-        P, p = self.P, self.p
-        need = torch.tensor([floats], dtype=torch.int64, device=self.ex.device)
-        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.ex.group)
-        floats = int(need.item())
-        if floats <= self.capacity_floats:
-            return
-        torch.cuda.synchronize()
-        dist.barrier(group=self.ex.group)
-        if self._peers:
-            for j, (w, f) in enumerate(self._peers):
-                if j != p:
-                    L.nts_ipc_close_handle(w)
-                    L.nts_ipc_close_handle(f)
-        if self.window:
-            L.nts_free_device(self.window)
-        self.window = L.nts_malloc_device(floats * 4)
-        if not self.window:
-            raise _lib.NtsError("window allocation failed: " + L.nts_last_error().decode())
-        self.capacity_floats = floats
-        handles = [None] * P
-        dist.all_gather_object(handles, (self._export(self.window), self._handle_flags), group=self.ex.group)
-        self._peers = []
-        for j in range(P):
-            if j == p:
-                self._peers.append((self.window, self.flags))
-            else:
-                w = L.nts_ipc_open_handle(handles[j][0])
-                f = L.nts_ipc_open_handle(handles[j][1])
-                if not w or not f:
-                    raise _lib.NtsError("cudaIpcOpenMemHandle failed: " + L.nts_last_error().decode())
-                self._peers.append((w, f))
-        dist.barrier(group=self.ex.group)
-
-    def peer_ptr(self, j):
-        return self._peers[j][0]
-
-    def reserve(self, owned_rows, recv_rows, F):
-        """Make sure the window holds max(owned_rows, recv_rows) x F floats on every rank (collective, first use
-        of a feature width only)."""
+    def reserve(self, F):
+        """Make the exported window large enough for feature width F on EVERY rank (collective on first use of a
+        width), exchange the IPC handles and (re)open the peers' windows."""
+        import ctypes as C
         if F in self._reserved:
             return
-        self._ensure(max(owned_rows, recv_rows, 1) * F)
+        L = _lib.load()
+        ex = self.ex
+        need = torch.tensor([L.nts_exchange_required_floats(self.handle, F)], dtype=torch.int64, device=ex.device)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=ex.group)
+        realloc = C.c_int(0)
+        _lib.call("nts_exchange_reserve", self.handle, int(need.item()), C.byref(realloc))
+        flag = torch.tensor([realloc.value], dtype=torch.int64, device=ex.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=ex.group)
+        if flag.item():
+            wh, fh = C.create_string_buffer(64), C.create_string_buffer(64)
+            _lib.call("nts_exchange_handles", self.handle, wh, fh)
+            handles = [None] * ex.P
+            dist.all_gather_object(handles, (bytes(wh.raw), bytes(fh.raw)), group=ex.group)
+            _lib.call("nts_exchange_open_peers", self.handle, b"".join(h[0] for h in handles),
+                      b"".join(h[1] for h in handles))
+            dist.barrier(group=ex.group)
         self._reserved.add(F)
 
-    def window_rows(self, rows, F):
-        arr = _WindowArray(self.window, max(rows, 1) * F)
-        return torch.as_tensor(arr, device=self.ex.device).view(torch.float32)[: rows * F].view(rows, F)
-
-    def begin(self, stream):
-        """Open a new publication epoch: wait (on `stream`) until every peer has consumed my previous one."""
-        self.epoch += 1
-        e = self.epoch
-        if e > 1:
-            for j in range(self.P):
-                if j != self.p:
-                    _lib.call("nts_signal_wait_geq", self.flags + 4 * (1 + j), e - 1, stream.cuda_stream)
-        return e
-
-    def commit(self, epoch, stream):
-        """Everything written to the window so far on `stream` becomes visible to the peers."""
-        _lib.call("nts_signal_set", self.flags, epoch, stream.cuda_stream)
-
-    def wait_published(self, j, epoch, stream):
-        _lib.call("nts_signal_wait_geq", self._peers[j][1], epoch, stream.cuda_stream)
-
-    def signal_consumed(self, epoch, stream):
-        """Tell every peer I am done reading its window for this epoch: set consumed[me] in THEIR flag array."""
-        for j in range(self.P):
-            if j != self.p:
-                _lib.call("nts_signal_set", self._peers[j][1] + 4 * (1 + self.p), epoch, stream.cuda_stream)
-
-
-class _WindowArray:
-    """__cuda_array_interface__ view of a raw device allocation (bytes as uint8 -> viewed as float32)."""
-
-    def __init__(self, ptr, floats):
-        self.__cuda_array_interface__ = {
-            "shape": (floats * 4,), "typestr": "|u1", "data": (int(ptr), False), "version": 2,
-        }
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().nts_exchange_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 _default = {}
