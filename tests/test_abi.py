@@ -1,9 +1,7 @@
 """CPU-only checks of the drop-in boundary: the shared object loads and exports every symbol that
 include/nts_b200.h declares, the ctypes table covers the header, and the product has no CPU fallback."""
-import ctypes
 import os
 
-import numpy as np
 import pytest
 
 from neutronstarlite_b200 import _lib
