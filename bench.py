@@ -501,8 +501,19 @@ def reference_gpu_kernels(pg, feats, layers, torch):
         ops.gather_by_dst_from_src(c, mine, x)
         torch.cuda.synchronize()
         err = float(((mine - y).abs().max() / y.abs().max().clamp(min=1e-30)).item())
+        # who is right where they differ?  float64 truth for the highest-degree destination (8 columns): the
+        # reference accumulates that row's millions of edges sequentially in fp32
+        co = c.column_offset_gpu.long()
+        hub = int(torch.argmax(co[1:] - co[:-1]).item())
+        e0, e1 = int(co[hub].item()), int(co[hub + 1].item())
+        srcs = c.row_indices_gpu[e0:e1].long() - c.src_range[0]
+        truth = (x[srcs, :8].double() * c.edge_weight_forward_gpu[e0:e1].double()[:, None]).sum(0)
+        scale = truth.abs().max().clamp(min=1e-30)
         key = "F%d_%s" % (F, "optim_nts" if optim else "plain")
         out[key] = {"avg_ms": sum(times) / len(times), "max_rel_diff_vs_ours": err,
+                    "hub_row_degree": e1 - e0,
+                    "hub_row_rel_err_vs_f64": {"ours": float(((mine[hub, :8].double() - truth).abs().max() / scale).item()),
+                                               "reference": float(((y[hub, :8].double() - truth).abs().max() / scale).item())},
                     "gedges_per_s": c.edge_size / (sum(times) / len(times) * 1e-3) / 1e9}
     return out
 
