@@ -356,6 +356,176 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// Same statistics with all lanes busy when H divides 32: lane = (edge slot, head), i.e. 32/H edges x H heads per
+// step, and the per-head reductions are xor-shuffles over the lanes that share a head (offsets >= H).
+template <int H>
+__global__ void __launch_bounds__(kThreads)
+    gat_softmax_stats_heads_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum,
+                                   const float *__restrict__ s_att, const float *__restrict__ d_att,
+                                   const uint32_t *__restrict__ row_idx, const uint32_t *__restrict__ off,
+                                   const uint32_t *__restrict__ mirror_index, uint32_t n_rows, float slope) {
+  static_assert(32 % H == 0, "H must divide the warp size");
+  constexpr uint32_t kEdgesPerStep = 32 / H;
+  __shared__ float scratch[kWarps][32];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t h = lane % H, el = lane / H;
+  const uint32_t r0 = blockIdx.x * kRowsPerCta;
+  const uint32_t r1 = min(n_rows, r0 + kRowsPerCta);
+  auto head_max = [](float v) {
+#pragma unroll
+    for (int o = 16; o >= H; o >>= 1)
+      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  };
+  auto head_sum = [](float v) {
+#pragma unroll
+    for (int o = 16; o >= H; o >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  for (uint32_t r = r0; r < r1; r++) {
+    const uint32_t b = __ldg(off + r), e = __ldg(off + r + 1);
+    const uint32_t deg = e - b;
+    const bool hub = deg > kHubDegree; // block-uniform
+    if (!hub && ((r - r0) % kWarps) != wid)
+      continue;
+    if (deg == 0) {
+      if (lane < H) {
+        seg_max[(size_t)r * H + lane] = 0.f;
+        seg_sum[(size_t)r * H + lane] = 1.f;
+      }
+      continue;
+    }
+    const uint32_t first = (hub ? wid * kEdgesPerStep : 0u) + el;
+    const uint32_t step = hub ? kWarps * kEdgesPerStep : kEdgesPerStep;
+    const float dv = __ldg(d_att + (size_t)r * H + h);
+    float mx = -INFINITY;
+    for (uint32_t i = first; i < deg; i += step) {
+      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+      mx = fmaxf(mx, leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope));
+    }
+    mx = head_max(mx);
+    if (hub) {
+      __syncthreads();
+      scratch[wid][lane] = mx;
+      __syncthreads();
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; w2++)
+        mx = fmaxf(mx, scratch[w2][h]);
+    }
+    float sum = 0.f;
+    for (uint32_t i = first; i < deg; i += step) {
+      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+      sum += expf(leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope) - mx);
+    }
+    sum = head_sum(sum);
+    if (hub) {
+      __syncthreads();
+      scratch[wid][lane] = sum;
+      __syncthreads();
+      sum = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; w2++)
+        sum += scratch[w2][h];
+    }
+    if (lane < H && (!hub || wid == 0)) {
+      seg_max[(size_t)r * H + lane] = mx;
+      seg_sum[(size_t)r * H + lane] = sum;
+    }
+  }
+}
+
+// Single-pass backward when a head is a power-of-two number of vectors <= 32 (e.g. 8 heads x 8 columns): every lane
+// owns vector column(s) c = lane + 32k of the row, its head is c / head_vecs, per-head dot products are segmented
+// xor-shuffle reductions, the first lane of each head group issues the score-gradient atomics.
+template <int VEC, int KB>
+__global__ void __launch_bounds__(kThreads)
+    gat_fused_backward_seg_kernel(float *__restrict__ mirror_grad, float *__restrict__ s_grad,
+                                  float *__restrict__ d_grad, const float *__restrict__ mirror,
+                                  const float *__restrict__ s_att, const float *__restrict__ d_att,
+                                  const float *__restrict__ seg_max, const float *__restrict__ seg_sum,
+                                  const float *__restrict__ out_dot_g, const float *__restrict__ g,
+                                  const uint32_t *__restrict__ row_idx, const uint32_t *__restrict__ off,
+                                  const uint32_t *__restrict__ mirror_index, uint32_t n_rows, uint32_t F, uint32_t H,
+                                  float slope) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nvec = F / VEC;
+  const uint32_t head_vecs = nvec / H; // power of two, <= 32
+  const bool leader = (lane % head_vecs) == 0;
+  uint32_t hk[KB];
+  bool act[KB];
+#pragma unroll
+  for (int k = 0; k < KB; k++) {
+    act[k] = lane + 32 * k < nvec;
+    hk[k] = act[k] ? (lane + 32 * k) / head_vecs : 0u;
+  }
+  const uint32_t n_edges = __ldg(off + n_rows);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kEdgeQuantum < n_edges; qw += nwarps) {
+    const uint32_t e0 = (uint32_t)(qw * kEdgeQuantum);
+    const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kEdgeQuantum);
+    uint32_t row = eo_find_row(off, n_rows, e0);
+    uint32_t row_end = __ldg(off + row + 1);
+    float d_acc[KB], dv[KB], mv[KB], iz[KB], og[KB];
+    auto load_row = [&]() {
+#pragma unroll
+      for (int k = 0; k < KB; k++) {
+        const size_t rh = (size_t)row * H + hk[k];
+        dv[k] = __ldg(d_att + rh);
+        mv[k] = __ldg(seg_max + rh);
+        iz[k] = 1.f / __ldg(seg_sum + rh);
+        og[k] = __ldg(out_dot_g + rh);
+        d_acc[k] = 0.f;
+      }
+    };
+    auto flush_row = [&]() {
+#pragma unroll
+      for (int k = 0; k < KB; k++)
+        if (act[k] && leader && d_acc[k] != 0.f)
+          atomicAdd(d_grad + (size_t)row * H + hk[k], d_acc[k]);
+    };
+    load_row();
+    for (uint32_t e = e0; e < e1; e++) {
+      if (e >= row_end) {
+        flush_row();
+        do {
+          row++;
+          row_end = __ldg(off + row + 1);
+        } while (e >= row_end);
+        load_row();
+      }
+      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
+      const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F);
+      const V *mm = reinterpret_cast<const V *>(mirror + (size_t)slot * F);
+      V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F);
+#pragma unroll
+      for (int k = 0; k < KB; k++) {
+        const uint32_t c = lane + 32 * k;
+        float dot = 0.f, pre = 0.f, a = 0.f;
+        V gv;
+        memset(&gv, 0, sizeof(V));
+        if (act[k]) {
+          gv = __ldg(gm + c);
+          dot = vec_dot(__ldg(mm + c), gv);
+          pre = __ldg(s_att + (size_t)slot * H + hk[k]) + dv[k];
+          a = expf(leaky(pre, slope) - mv[k]) * iz[k];
+          vec_red_add<VEC>(dm + c, vec_scale(gv, a));
+        }
+        // per-head dot: lanes of one head are contiguous and head_vecs is a power of two
+        for (uint32_t o = head_vecs >> 1; o > 0; o >>= 1)
+          dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (act[k] && leader) {
+          const float d_pre = a * (dot - og[k]) * (pre > 0.f ? 1.f : slope);
+          atomicAdd(s_grad + (size_t)slot * H + hk[k], d_pre);
+          d_acc[k] += d_pre;
+        }
+      }
+    }
+    flush_row();
+  } // quantum loop
+}
+
 // backward of the fused layer, one pass over the edges:
 //   a        = exp(logit - m) / z                              (recomputed)
 //   d_a      = < mirror[slot, head h], g[dst, head h] >        (warp-shuffle reduction)
@@ -666,9 +836,24 @@ int nts_gat_softmax_stats(float *seg_max, float *seg_sum, const float *src_score
   NTS_ARG_CHECK(seg_max && seg_sum && src_score && dst_score && row_indices && column_offset && mirror_index,
                 "null pointer passed to gat_softmax_stats");
   unsigned grid = (batch_size + kRowsPerCta - 1) / kRowsPerCta;
-  gat_softmax_stats_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(seg_max, seg_sum, src_score, dst_score,
-                                                                     row_indices, column_offset, mirror_index,
-                                                                     batch_size, heads, negative_slope);
+  cudaStream_t st = as_stream(stream);
+#define NTS_STATS(H_)                                                                                           \
+  gat_softmax_stats_heads_kernel<H_><<<grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,        \
+                                                                  row_indices, column_offset, mirror_index,      \
+                                                                  batch_size, negative_slope)
+  switch (heads) { // all lanes busy when the head count divides the warp
+  case 1: NTS_STATS(1); break;
+  case 2: NTS_STATS(2); break;
+  case 4: NTS_STATS(4); break;
+  case 8: NTS_STATS(8); break;
+  case 16: NTS_STATS(16); break;
+  case 32: NTS_STATS(32); break;
+  default:
+    gat_softmax_stats_kernel<<<grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score, row_indices,
+                                                        column_offset, mirror_index, batch_size, heads,
+                                                        negative_slope);
+  }
+#undef NTS_STATS
   NTS_LAUNCH_CHECK();
   return 0;
 }
@@ -691,6 +876,40 @@ int nts_gat_fused_aggregate_backward(float *mirror_grad, float *src_score_grad, 
   while (vec > 1 && (feature_size / heads) % vec != 0)
     vec >>= 1;
   unsigned grid = full_grid();
+  // single-pass kernel: prefer the vector width that keeps the most lanes busy, needs a power-of-two number of
+  // vectors per head (<= 32) and at most 4 chunks per lane
+  {
+    int sv = vec;
+    while (sv > 1 && feature_size / sv < 32)
+      sv >>= 1;
+    const uint32_t nvec = feature_size / sv, hv = nvec / heads;
+    const bool pow2 = hv >= 1 && (hv & (hv - 1)) == 0 && hv <= 32 && hv * heads == nvec;
+    const uint32_t kb = (nvec + 31) / 32;
+    if (pow2 && kb <= 4) {
+#define NTS_GATS(V_, K_)                                                                                         \
+  gat_fused_backward_seg_kernel<V_, K_><<<grid, kThreads, 0, st>>>(                                              \
+      mirror_grad, src_score_grad, dst_score_grad, mirror, src_score, dst_score, seg_max, seg_sum, out_dot_grad, \
+      dst_grad, row_indices, column_offset, mirror_index, batch_size, feature_size, heads, negative_slope)
+#define NTS_GATS_K(V_)                                                                                           \
+  if (kb == 1)                                                                                                   \
+    NTS_GATS(V_, 1);                                                                                             \
+  else if (kb == 2)                                                                                              \
+    NTS_GATS(V_, 2);                                                                                             \
+  else                                                                                                           \
+    NTS_GATS(V_, 4)
+      if (sv == 4) {
+        NTS_GATS_K(4);
+      } else if (sv == 2) {
+        NTS_GATS_K(2);
+      } else {
+        NTS_GATS_K(1);
+      }
+#undef NTS_GATS_K
+#undef NTS_GATS
+      NTS_LAUNCH_CHECK();
+      return 0;
+    }
+  }
 #define NTS_GATB(V_)                                                                                           \
   gat_fused_backward_kernel<V_><<<grid, kThreads, 0, st>>>(mirror_grad, src_score_grad, dst_score_grad, mirror, \
                                                            src_score, dst_score, seg_max, seg_sum, out_dot_grad, \

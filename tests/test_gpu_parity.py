@@ -446,3 +446,49 @@ def test_offsets_beyond_32_bits():
     close(out.cpu().numpy(), ref)
     del x
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("H,D", [(8, 8), (8, 64), (1, 64), (3, 5), (2, 16), (1, 41), (16, 4)])
+def test_fully_fused_gat_layer_vs_operator_chain(H, D):
+    """K7 (stats + attention-weighted aggregation + single-pass backward) against the chain of individually tested
+    operators (scatter-src / scatter-dst / leaky-relu / edge-softmax / fused aggregation) on a graph with a hub
+    segment longer than the block-cooperative threshold."""
+    from neutronstarlite_b200 import ops
+    from neutronstarlite_b200.graph import PartitionedGraph
+    rng = np.random.default_rng(H * 1000 + D)
+    Vp, Vg, E = 500, 1500, 30000
+    off, idx, _ = random_csr(Vp, Vg, E, seed=H * 7 + D, hub_rows=1)
+    used = np.unique(idx)
+    mi = np.zeros(Vg + 1, dtype=np.uint32)
+    mi[used + 1] = 1
+    mi = np.cumsum(mi, dtype=np.uint32)
+    M = int(mi[-1])
+    F = H * D
+    pg = PartitionedGraph(None, 1, 0, np.array([0, Vp], dtype=np.uint32))
+    pg.owned_vertices, pg.owned_edges, pg.owned_mirrors = Vp, E, M
+    pg.column_offset_gpu, pg.row_indices_gpu, pg.mirror_index_gpu = up_u32(off), up_u32(idx), up_u32(mi)
+    mirror = up(rng.uniform(-1, 1, (M, F)).astype(np.float32))
+    s_att = up(rng.uniform(-2, 2, (M, H)).astype(np.float32))
+    d_att = up(rng.uniform(-2, 2, (Vp, H)).astype(np.float32))
+    g = up(rng.uniform(-1, 1, (Vp, F)).astype(np.float32))
+    # operator chain
+    sc_s, sc_d, sm, fw = ops.DistGPUScatterSrc(pg), ops.DistGPUScatterDst(pg), ops.DistGPUEdgeSoftMax(pg), \
+        ops.DistGPUAggregateDstFuseWeight(pg)
+    pre = sc_s.forward(s_att) + sc_d.forward(d_att)
+    logit = torch.nn.functional.leaky_relu(pre, 0.2)
+    a = sm.forward(logit)
+    out_ref = fw.forward(mirror, a)
+    dm_ref = fw.backward(g)
+    d_logit = sm.backward(fw.get_additional_grad())
+    d_pre = d_logit * torch.where(pre > 0, torch.ones_like(pre), torch.full_like(pre, 0.2))
+    ds_ref = sc_s.backward(d_pre.contiguous())
+    dd_ref = sc_d.backward(d_pre.contiguous())
+    # K7
+    fused = ops.DistGPUFusedGATOp(pg, negative_slope=0.2)
+    out = fused.forward(mirror, s_att, d_att)
+    dm, ds, dd = fused.backward(g)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, out_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dm, dm_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ds, ds_ref, rtol=1e-3, atol=2e-5)
+    torch.testing.assert_close(dd, dd_ref, rtol=1e-3, atol=2e-5)
