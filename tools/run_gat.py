@@ -51,6 +51,17 @@ def main():
     for _ in range(a.warmup):
         model.run_epoch()
     torch.cuda.synchronize()
+    # per-entry-point device time (CUDA events around every C-ABI call; nothing is synchronised until the end)
+    records = []
+    raw_call = _lib.call
+
+    def timed_call(name, *args):
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record()
+        raw_call(name, *args)
+        e_b.record()
+        records.append((name, e_a, e_b))
+    _lib.call = timed_call
     l0 = _lib.load().nts_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -59,6 +70,10 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    _lib.call = raw_call
+    per_call = {}
+    for name, e_a, e_b in records:
+        per_call[name] = per_call.get(name, 0.0) + e_a.elapsed_time(e_b) / a.steps
     n_layers = len(layers) - 1
     print(json.dumps({
         "workload": "%s-shaped, %d V, %d E, %d-layer GAT %s, %d heads (hidden layers), %s" % (
@@ -66,6 +81,7 @@ def main():
             "K7 fully fused attention+aggregation" if a.fused_kernel else "[E,H] operator chain + fused aggregation"),
         "ms_per_epoch": ms, "epochs_per_sec": 1e3 / ms,
         "aggregated_edges_per_sec": 2 * n_layers * E / (ms * 1e-3),
+        "ms_per_epoch_by_entry_point": {k: round(v, 3) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1])},
         "loss": float(loss.item()), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
         "gpu_launches_per_epoch": (_lib.load().nts_kernel_launch_count() - l0) / a.steps}))
 
