@@ -363,10 +363,10 @@ __global__ void __launch_bounds__(kThreads)
     gat_softmax_stats_heads_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum,
                                    const float *__restrict__ s_att, const float *__restrict__ d_att,
                                    const uint32_t *__restrict__ row_idx, const uint32_t *__restrict__ off,
-                                   const uint32_t *__restrict__ mirror_index, uint32_t n_rows, float slope) {
+                                   const uint32_t *__restrict__ mirror_index, uint32_t n_rows, float slope,
+                                   int split_hubs) {
   static_assert(32 % H == 0, "H must divide the warp size");
   constexpr uint32_t kEdgesPerStep = 32 / H;
-  __shared__ float scratch[kWarps][32];
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t h = lane % H, el = lane / H;
   const uint32_t r0 = blockIdx.x * kRowsPerCta;
@@ -387,17 +387,19 @@ __global__ void __launch_bounds__(kThreads)
     const uint32_t b = __ldg(off + r), e = __ldg(off + r + 1);
     const uint32_t deg = e - b;
     const bool hub = deg > kHubDegree; // block-uniform
-    if (!hub && ((r - r0) % kWarps) != wid)
+    if (((r - r0) % kWarps) != wid)
       continue;
-    if (deg == 0) {
+    if (deg == 0 || (hub && split_hubs)) {
+      // empty segment: (0, 1) so consumers never divide by zero; hub: identity of (max, sum), the segment is
+      // reduced by gat_hub_stats_kernel with many CTAs per row
       if (lane < H) {
-        seg_max[(size_t)r * H + lane] = 0.f;
-        seg_sum[(size_t)r * H + lane] = 1.f;
+        seg_max[(size_t)r * H + lane] = deg == 0 ? 0.f : -INFINITY;
+        seg_sum[(size_t)r * H + lane] = deg == 0 ? 1.f : 0.f;
       }
       continue;
     }
-    const uint32_t first = (hub ? wid * kEdgesPerStep : 0u) + el;
-    const uint32_t step = hub ? kWarps * kEdgesPerStep : kEdgesPerStep;
+    const uint32_t first = el;
+    const uint32_t step = kEdgesPerStep;
     const float dv = __ldg(d_att + (size_t)r * H + h);
     float mx = -INFINITY;
     for (uint32_t i = first; i < deg; i += step) {
@@ -405,32 +407,80 @@ __global__ void __launch_bounds__(kThreads)
       mx = fmaxf(mx, leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope));
     }
     mx = head_max(mx);
-    if (hub) {
-      __syncthreads();
-      scratch[wid][lane] = mx;
-      __syncthreads();
-#pragma unroll
-      for (int w2 = 0; w2 < kWarps; w2++)
-        mx = fmaxf(mx, scratch[w2][h]);
-    }
     float sum = 0.f;
     for (uint32_t i = first; i < deg; i += step) {
       const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
       sum += expf(leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope) - mx);
     }
     sum = head_sum(sum);
-    if (hub) {
-      __syncthreads();
-      scratch[wid][lane] = sum;
-      __syncthreads();
-      sum = 0.f;
-#pragma unroll
-      for (int w2 = 0; w2 < kWarps; w2++)
-        sum += scratch[w2][h];
-    }
-    if (lane < H && (!hub || wid == 0)) {
+    if (lane < H) {
       seg_max[(size_t)r * H + lane] = mx;
       seg_sum[(size_t)r * H + lane] = sum;
+    }
+  }
+}
+
+// Hub segments (> kHubDegree edges; the Zipf generator gives one destination 8.9 M in-edges) are split over
+// kHubSplit CTAs per row: grid = (row blocks, kHubSplit); a CTA looks at the rows of its block and, for hub rows
+// only, reduces its slice of the segment and merges with one atomic per head.  PASS 0: maximum, PASS 1: sum of
+// exp(logit - max) (the maxima must be complete first, hence two launches).
+constexpr uint32_t kHubSplit = 64;
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  int *a = reinterpret_cast<int *>(addr);
+  int old = *a;
+  while (__int_as_float(old) < v) {
+    const int assumed = old;
+    old = atomicCAS(a, assumed, __float_as_int(v));
+    if (old == assumed)
+      break;
+  }
+}
+
+template <int H, int PASS>
+__global__ void __launch_bounds__(kThreads)
+    gat_hub_stats_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum, const float *__restrict__ s_att,
+                         const float *__restrict__ d_att, const uint32_t *__restrict__ row_idx,
+                         const uint32_t *__restrict__ off, const uint32_t *__restrict__ mirror_index, uint32_t n_rows,
+                         float slope) {
+  static_assert(32 % H == 0, "H must divide the warp size");
+  constexpr uint32_t kEdgesPerStep = 32 / H;
+  __shared__ float scratch[kWarps][32];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t h = lane % H, el = lane / H;
+  const uint32_t r0 = blockIdx.x * kRowsPerCta;
+  const uint32_t r1 = min(n_rows, r0 + kRowsPerCta);
+  for (uint32_t r = r0; r < r1; r++) {
+    const uint32_t b = __ldg(off + r), e = __ldg(off + r + 1);
+    const uint32_t deg = e - b;
+    if (deg <= kHubDegree)
+      continue; // block-uniform
+    const uint32_t per = (deg + kHubSplit - 1) / kHubSplit;
+    const uint32_t lo = min(deg, blockIdx.y * per), hi = min(deg, lo + per);
+    const float dv = __ldg(d_att + (size_t)r * H + h);
+    const float mx_all = PASS == 1 ? __ldg(seg_max + (size_t)r * H + h) : 0.f;
+    float acc = PASS == 0 ? -INFINITY : 0.f;
+    for (uint32_t i = lo + wid * kEdgesPerStep + el; i < hi; i += kWarps * kEdgesPerStep) {
+      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+      const float x = leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope);
+      acc = PASS == 0 ? fmaxf(acc, x) : acc + expf(x - mx_all);
+    }
+#pragma unroll
+    for (int o = 16; o >= H; o >>= 1) {
+      const float other = __shfl_xor_sync(0xffffffffu, acc, o);
+      acc = PASS == 0 ? fmaxf(acc, other) : acc + other;
+    }
+    __syncthreads();
+    scratch[wid][lane] = acc;
+    __syncthreads();
+    if (wid == 0 && lane < H) {
+      float v = scratch[0][lane];
+#pragma unroll
+      for (int w2 = 1; w2 < kWarps; w2++)
+        v = PASS == 0 ? fmaxf(v, scratch[w2][lane]) : v + scratch[w2][lane];
+      if (PASS == 0)
+        atomic_max_float(seg_max + (size_t)r * H + lane, v);
+      else if (v != 0.f)
+        atomicAdd(seg_sum + (size_t)r * H + lane, v);
     }
   }
 }
@@ -486,39 +536,66 @@ __global__ void __launch_bounds__(kThreads)
           atomicAdd(d_grad + (size_t)row * H + hk[k], d_acc[k]);
     };
     load_row();
-    for (uint32_t e = e0; e < e1; e++) {
-      if (e >= row_end) {
-        flush_row();
-        do {
-          row++;
-          row_end = __ldg(off + row + 1);
-        } while (e >= row_end);
-        load_row();
-      }
-      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
-      const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F);
-      const V *mm = reinterpret_cast<const V *>(mirror + (size_t)slot * F);
-      V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F);
+    for (uint32_t eb = e0; eb < e1; eb += 32) {
+      // indices and mirror slots of 32 edges at once (coalesced), broadcast per edge by shuffle; the mirror row of
+      // edge j+1 is requested before edge j is processed (the random gather is the long-latency load)
+      const uint32_t cnt = min(32u, e1 - eb);
+      uint32_t my_slot = 0;
+      if (lane < cnt)
+        my_slot = __ldg(mirror_index + __ldg(row_idx + eb + lane));
+      V m_next[KB];
+      {
+        const uint32_t s0 = __shfl_sync(0xffffffffu, my_slot, 0);
+        const V *mm0 = reinterpret_cast<const V *>(mirror + (size_t)s0 * F);
 #pragma unroll
-      for (int k = 0; k < KB; k++) {
-        const uint32_t c = lane + 32 * k;
-        float dot = 0.f, pre = 0.f, a = 0.f;
-        V gv;
-        memset(&gv, 0, sizeof(V));
-        if (act[k]) {
-          gv = __ldg(gm + c);
-          dot = vec_dot(__ldg(mm + c), gv);
-          pre = __ldg(s_att + (size_t)slot * H + hk[k]) + dv[k];
-          a = expf(leaky(pre, slope) - mv[k]) * iz[k];
-          vec_red_add<VEC>(dm + c, vec_scale(gv, a));
+        for (int k = 0; k < KB; k++)
+          if (act[k])
+            m_next[k] = __ldg(mm0 + lane + 32 * k);
+      }
+      for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t e = eb + j;
+        if (e >= row_end) {
+          flush_row();
+          do {
+            row++;
+            row_end = __ldg(off + row + 1);
+          } while (e >= row_end);
+          load_row();
         }
-        // per-head dot: lanes of one head are contiguous and head_vecs is a power of two
-        for (uint32_t o = head_vecs >> 1; o > 0; o >>= 1)
-          dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        if (act[k] && leader) {
-          const float d_pre = a * (dot - og[k]) * (pre > 0.f ? 1.f : slope);
-          atomicAdd(s_grad + (size_t)slot * H + hk[k], d_pre);
-          d_acc[k] += d_pre;
+        const uint32_t slot = __shfl_sync(0xffffffffu, my_slot, j);
+        V m_cur[KB];
+#pragma unroll
+        for (int k = 0; k < KB; k++)
+          m_cur[k] = m_next[k];
+        if (j + 1 < cnt) {
+          const uint32_t s1 = __shfl_sync(0xffffffffu, my_slot, j + 1);
+          const V *mm1 = reinterpret_cast<const V *>(mirror + (size_t)s1 * F);
+#pragma unroll
+          for (int k = 0; k < KB; k++)
+            if (act[k])
+              m_next[k] = __ldg(mm1 + lane + 32 * k);
+        }
+        const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F);
+        V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F);
+#pragma unroll
+        for (int k = 0; k < KB; k++) {
+          const uint32_t c = lane + 32 * k;
+          float dot = 0.f, pre = 0.f, a = 0.f;
+          if (act[k]) {
+            const V gv = __ldg(gm + c);
+            dot = vec_dot(m_cur[k], gv);
+            pre = __ldg(s_att + (size_t)slot * H + hk[k]) + dv[k];
+            a = expf(leaky(pre, slope) - mv[k]) * iz[k];
+            vec_red_add<VEC>(dm + c, vec_scale(gv, a));
+          }
+          // per-head dot: lanes of one head are contiguous and head_vecs is a power of two
+          for (uint32_t o = head_vecs >> 1; o > 0; o >>= 1)
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          if (act[k] && leader) {
+            const float d_pre = a * (dot - og[k]) * (pre > 0.f ? 1.f : slope);
+            atomicAdd(s_grad + (size_t)slot * H + hk[k], d_pre);
+            d_acc[k] += d_pre;
+          }
         }
       }
     }
@@ -837,10 +914,21 @@ int nts_gat_softmax_stats(float *seg_max, float *seg_sum, const float *src_score
                 "null pointer passed to gat_softmax_stats");
   unsigned grid = (batch_size + kRowsPerCta - 1) / kRowsPerCta;
   cudaStream_t st = as_stream(stream);
+  const dim3 hub_grid(grid, kHubSplit);
 #define NTS_STATS(H_)                                                                                           \
-  gat_softmax_stats_heads_kernel<H_><<<grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,        \
-                                                                  row_indices, column_offset, mirror_index,      \
-                                                                  batch_size, negative_slope)
+  do {                                                                                                          \
+    gat_softmax_stats_heads_kernel<H_><<<grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,      \
+                                                                    row_indices, column_offset, mirror_index,    \
+                                                                    batch_size, negative_slope, 1);              \
+    count_launch();                                                                                             \
+    gat_hub_stats_kernel<H_, 0><<<hub_grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,         \
+                                                                 row_indices, column_offset, mirror_index,       \
+                                                                 batch_size, negative_slope);                    \
+    count_launch();                                                                                             \
+    gat_hub_stats_kernel<H_, 1><<<hub_grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,         \
+                                                                 row_indices, column_offset, mirror_index,       \
+                                                                 batch_size, negative_slope);                    \
+  } while (0)
   switch (heads) { // all lanes busy when the head count divides the warp
   case 1: NTS_STATS(1); break;
   case 2: NTS_STATS(2); break;
