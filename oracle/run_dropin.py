@@ -64,11 +64,88 @@ def run(binary, algo, epochs, layers="1433-128-7", timeout=600):
             "raw_passed_lines": [ln for ln in out.splitlines() if "pass" in ln.lower()][:12]}
 
 
+SYN_CFG = """ALGORITHM:{algo}
+VERTICES:{V}
+LAYERS:{layers}
+EPOCHS:{epochs}
+EDGE_FILE:{edge}
+FEATURE_FILE:random
+LABEL_FILE:random
+MASK_FILE:random
+PROC_OVERLAP:0
+PROC_LOCAL:0
+PROC_CUDA:1
+PROC_REP:0
+LOCK_FREE:1
+LEARN_RATE:0.01
+WEIGHT_DECAY:0.0001
+DECAY_RATE:0.97
+DECAY_EPOCH:100
+DROP_RATE:0.0
+"""
+
+
+def run_synthetic(binary, algo, V, layers, edge_file, epochs, timeout=1500):
+    """Per-epoch seconds of a reference toolkit on a synthetic edge file: from its own `Times[...(s)]` print when the
+    toolkit has one (GCN_EAGER_single.hpp:250-252), else from the arrival times of its per-epoch loss lines."""
+    import time
+    with tempfile.TemporaryDirectory() as d:
+        cfg = os.path.join(d, "c.cfg")
+        open(cfg, "w").write(SYN_CFG.format(algo=algo, V=V, layers=layers, epochs=epochs, edge=edge_file))
+        env = dict(os.environ)
+        env.setdefault("NTS_THREADS", str(os.cpu_count()))
+        env["OMP_NUM_THREADS"] = env["NTS_THREADS"]
+        t0 = time.perf_counter()
+        p = subprocess.Popen([binary, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+        stamps, own = [], []
+        for line in p.stdout:
+            if "Running.Epoch[" in line:
+                stamps.append(time.perf_counter())
+                m = re.search(r"Times\[([0-9.eE+-]+)\(s\)\]", line)
+                if m:
+                    own.append(float(m.group(1)))
+        p.wait(timeout=timeout)
+        total = time.perf_counter() - t0
+    if own:
+        per = own[1:] if len(own) > 1 else own
+    else:
+        per = [b - a for a, b in zip(stamps[:-1], stamps[1:])]
+    return {"algo": algo, "rc": p.returncode, "epochs_seen": len(stamps), "s_per_epoch_after_first": per,
+            "s_per_epoch_median": sorted(per)[len(per) // 2] if per else None, "wall_s_incl_load": total}
+
+
+def synthetic_main(div, epochs):
+    """Reference host code + OUR kernels (nts_dropin_main) next to reference host code + ITS OWN kernels
+    (nts_refgpu_main) on a Reddit-shaped synthetic edge file of 1/div of the edges."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.dirname(HERE))
+    from neutronstarlite_b200 import synth
+    V, E_rand, layers = synth.WORKLOADS["reddit"]
+    src, dst = synth.zipf_edges(V, E_rand // div, torch.device("cpu"))
+    with tempfile.TemporaryDirectory() as d:
+        efile = os.path.join(d, "syn.edge")
+        torch.stack([src, dst], 1).numpy().astype(np.uint32).tofile(efile)
+        res = {"graph": "reddit-shaped 1/%d: %d V, %d E, LAYERS %s" % (div, V, int(src.numel()), "-".join(map(str, layers)))}
+        for name, binary in (("ours", os.path.join(REF, "nts_dropin_main")), ("reference_kernels", os.path.join(REF, "nts_refgpu_main"))):
+            if not os.path.exists(binary):
+                continue
+            for algo in ("GCNEAGERSINGLE", "GCN"):
+                res["%s_%s" % (name, algo)] = run_synthetic(binary, algo, V, "-".join(map(str, layers)), efile, epochs)
+    print(json.dumps(res, indent=1))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=30)
     ap.add_argument("--algos", default="GCNEAGERSINGLE,GCN,GATGPUDIST,test_getdep")
+    ap.add_argument("--synthetic", type=int, default=0, metavar="DIV",
+                    help="compare ours vs the reference's own kernels through the reference's host code on 1/DIV of "
+                         "the Reddit-shaped graph")
     a = ap.parse_args()
+    if a.synthetic:
+        return synthetic_main(a.synthetic, min(a.epochs, 6))
     res = {}
     cpu = os.path.join(REF, "nts_ref_main")
     gpu = os.path.join(REF, "nts_dropin_main")
