@@ -424,6 +424,9 @@ def main():
             ref_gpu = reference_gpu_kernels(pg, feats, layers, torch)
         except Exception as exc:  # baseline only: never fail the bench because of it
             ref_gpu = {"error": repr(exc)}
+    agg_ms = sum(d["ms"] for d in ksum.values()) / args.steps   # this rank's aggregation launches per step
+    agg_only = {"ms_per_step": agg_ms, "edges_per_s": 3.0 * E_total / (agg_ms * 1e-3) if agg_ms > 0 else None,
+                "note": "CUDA-event time of the aggregation launches only (rank 0), SURVEY 8d"}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -447,7 +450,7 @@ def main():
                            feats.numel() * 4 / 1e6, pg.owned_edges * 16 / 1e6),
                        "drop_rate": args.drop_rate, "kernel_variant": args.variant or 2, "zipf_s": args.zipf_s},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "kernels": kernels, "reference_gpu_kernels": ref_gpu, "clocks": clocks,
+            "kernels": kernels, "aggregation_only": agg_only, "reference_gpu_kernels": ref_gpu, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
