@@ -492,3 +492,50 @@ def test_fully_fused_gat_layer_vs_operator_chain(H, D):
     torch.testing.assert_close(dm, dm_ref, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(ds, ds_ref, rtol=1e-3, atol=2e-5)
     torch.testing.assert_close(dd, dd_ref, rtol=1e-3, atol=2e-5)
+
+
+def test_full_size_reddit_shaped_graph():
+    """Config B of BASELINE.json at FULL size (232 965 V, 114.8 M edges, F = 602 / 128): exact in-degree counts,
+    adjointness of forward / backward, and an independent float64 PyTorch reference (index_add over the edge list) on
+    an 8-column slice - the hub destination sums 8.9 M edges, so this also pins accuracy where fp32 order matters."""
+    from neutronstarlite_b200 import ops, synth
+    from neutronstarlite_b200.graph import PartitionedGraph
+    d = dev()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~25 GB of free device memory")
+    V, E_rand, layers = synth.WORKLOADS["reddit"]
+    src, dst = synth.zipf_edges(V, E_rand, d)
+    pg = PartitionedGraph.from_device_edges(src, dst, V)
+    c = pg.graph_chunks[0]
+    assert c.edge_size == E_rand + V
+    indeg = torch.bincount(dst, minlength=V)
+    assert int(indeg.max()) < (1 << 24)
+    del src, dst
+    F = layers[0]
+    ones = torch.ones((V, F), device=d)
+    y = torch.zeros((V, F), device=d)
+    ops.gather_by_dst_from_src(c, y, ones, with_weight=False)
+    assert torch.equal(y[:, 0], indeg.to(torch.float32)) and torch.equal(y[:, F - 1], indeg.to(torch.float32))
+    del ones
+    gen = torch.Generator(device=d).manual_seed(3)
+    x = torch.rand((V, F), generator=gen, device=d) * 2 - 1
+    y.zero_()
+    ops.gather_by_dst_from_src(c, y, x)
+    # float64 reference on 8 columns straight from the CSC arrays
+    col = c.column_offset_gpu.long()
+    dst_of_edge = torch.repeat_interleave(torch.arange(V, device=d), col[1:] - col[:-1])
+    srcs = c.row_indices_gpu.long()
+    ref = torch.zeros((V, 8), dtype=torch.float64, device=d)
+    ref.index_add_(0, dst_of_edge, x[srcs, :8].double() * c.edge_weight_forward_gpu.double()[:, None])
+    err = (y[:, :8].double() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 1e-4, float(err)
+    del ref, dst_of_edge, srcs
+    # adjointness at the second width: <A x, g> == <x, A^T g>
+    F2 = layers[1]
+    x2 = torch.rand((V, F2), generator=gen, device=d) * 2 - 1
+    g2 = torch.rand((V, F2), generator=gen, device=d) * 2 - 1
+    op = ops.ForwardSingleGPUfuseOp(pg)
+    lhs = (op.forward(x2).double() * g2.double()).sum()
+    rhs = (x2.double() * op.backward(g2).double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-6 * max(1.0, abs(float(lhs)))
