@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="aggregation kernel variant (0 auto, 1 shuffle, 2 bulk)")
     ap.add_argument("--edges-per-warp", type=int, default=0)
     ap.add_argument("--drop-rate", type=float, default=0.5)
+    ap.add_argument("--toolkit", default="gcn", choices=["gcn", "gcn_eager"],
+                    help="gcn = toolkits/GCN.hpp order (aggregate, then GEMM: the headline config); gcn_eager = "
+                         "toolkits/GCN_EAGER*.hpp order (GEMM, then aggregate the narrow result) - opt-in")
     ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline runs on E/div edges")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -261,7 +264,7 @@ def main():
     from neutronstarlite_b200 import _lib, ops
     from neutronstarlite_b200.exchange import GpuExchange
     from neutronstarlite_b200.graph import PartitionedGraph, partition_offsets_from_out_degree
-    from neutronstarlite_b200.toolkits import GCNImpl
+    from neutronstarlite_b200.toolkits import GCNImpl, GCNEagerImpl
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -302,7 +305,13 @@ def main():
         else:
             ex = GpuExchange(pg, transport=transport)
         op_kwargs["exchange"] = ex
-    model = GCNImpl(pg, layers, feats, labels, mask, drop_rate=args.drop_rate, op_kwargs=op_kwargs)
+    eager = args.toolkit == "gcn_eager"
+    model = (GCNEagerImpl if eager else GCNImpl)(pg, layers, feats, labels, mask, drop_rate=args.drop_rate,
+                                                  op_kwargs=op_kwargs)
+    n_layers = len(layers) - 1
+    # aggregation calls per epoch: GCN.hpp never back-propagates its first graph op (SURVEY 8 note) -> L + (L-1);
+    # the eager order starts with an NN op, so all L graph ops have a backward -> 2L
+    agg_calls = float(2 * n_layers if eager else 2 * n_layers - 1)
 
     def barrier():
         if world > 1:
@@ -341,7 +350,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = 3.0 * E_total / (ms_step * 1e-3)
+    value = agg_calls * E_total / (ms_step * 1e-3)
 
     # ---- timed region B: end to end through the public API with HOST buffers
     e2e = None
@@ -391,11 +400,11 @@ def main():
         hb = torch.tensor([feats.numel() * 4], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(hb)
-        e2e = {"value": 3.0 * E_total / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
+        e2e = {"value": agg_calls * E_total / (ms_e2e * 1e-3), "unit": "edges/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(hb.item()), "d2h_bytes_per_step": 4 * world}
 
     # ---- roofline of the dominant kernel: layer-0 forward aggregation (widest F), this rank's launches
-    F0 = layers[0]
+    F0 = layers[1] if eager else layers[0]
     k = ksum.get(("fwd", F0))
     roof = None
     if k and k["ms"] > 0:
@@ -425,11 +434,11 @@ def main():
         except Exception as exc:  # baseline only: never fail the bench because of it
             ref_gpu = {"error": repr(exc)}
     agg_ms = sum(d["ms"] for d in ksum.values()) / args.steps   # this rank's aggregation launches per step
-    agg_only = {"ms_per_step": agg_ms, "edges_per_s": 3.0 * E_total / (agg_ms * 1e-3) if agg_ms > 0 else None,
+    agg_only = {"ms_per_step": agg_ms, "edges_per_s": agg_calls * E_total / (agg_ms * 1e-3) if agg_ms > 0 else None,
                 "note": "CUDA-event time of the aggregation launches only (rank 0), SURVEY 8d"}
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not eager:   # the CPU arm is ALGORITHM:GCNCPU (gcn order)
             div = max(1, args.cpu_sample_div)
             edges = _sample_edges_cpu(V, E_rand, div)
             r = reference_cpu_epochs(V, layers, edges, 2, 1)
@@ -448,7 +457,8 @@ def main():
                        if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (features %.0f MB, graph arrays %.0f MB per rank)" % (
                            feats.numel() * 4 / 1e6, pg.owned_edges * 16 / 1e6),
-                       "drop_rate": args.drop_rate, "kernel_variant": args.variant or 2, "zipf_s": args.zipf_s},
+                       "drop_rate": args.drop_rate, "toolkit": args.toolkit,
+                       "aggregations_per_epoch": int(agg_calls), "kernel_variant": args.variant or 2, "zipf_s": args.zipf_s},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "kernels": kernels, "aggregation_only": agg_only, "reference_gpu_kernels": ref_gpu, "clocks": clocks,
         }

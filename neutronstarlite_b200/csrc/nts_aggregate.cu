@@ -19,7 +19,16 @@
 //   variant 1 (shuffle): each lane loads one edge's (index, weight) coalesced, broadcast by __shfl.
 //   variant 2 (bulk):    one thread per CTA issues `cp.async.bulk` (TMA, SASS UBLKCP) copies of the
 //                        CTA's index and weight tiles into shared memory, completion on an mbarrier;
-//                        warps then read (index, weight) with broadcast LDS.
+//                        warps then read (index, weight) with broadcast LDS.  DEFAULT (15.5 vs 31.3 ms
+//                        on the F=602 Reddit-shaped launch; profiles/README.md).
+//
+// Template parameters of segment_gather_sum_kernel<VEC,K,U,BULK,MINB,HM>: VEC floats per lane load, K vector
+// chunks per lane (a warp covers 32*VEC*K columns per tile), U edges whose loads are issued before their FMAs,
+// BULK = variant 2, MINB = __launch_bounds__ min CTAs/SM (register cap), HM = head mode: 0 one weight per edge,
+// 1 the weight array is [E,H] and each lane picks its column's head, 2 the weight is recomputed on the fly from the
+// per-vertex attention scores and softmax statistics (the fused GAT layer, nts_edge_ops.cu K7).
+// (U, MINB) per shape come from the sweeps in profiles/tune_r1_*.jsonl; NTS_AGG_TUNE / NTS_AGG_TILES are
+// measurement hooks read once at first launch, not product configuration.
 #include "nts_common.cuh"
 
 namespace nts {

@@ -160,6 +160,35 @@ class GCNImpl:
         return self.loss, acc
 
 
+class GCNEagerImpl(GCNImpl):
+    """Transform-then-aggregate GCN: toolkits/GCN_EAGER_single.hpp:184-232 (P = 1) and toolkits/GCN_EAGER.hpp (P > 1).
+    Each layer runs the weight GEMM first and aggregates the NARROW result (widths LAYERS[1:], e.g. 128 and 41
+    instead of 602 and 128 - 4.7x fewer gathered bytes on config B), then `log_softmax` + `nll_loss` on the last
+    aggregate.  The tape is [NNOP, GRAPHOP, NNOP, GRAPHOP, NNOP(loss)], so every aggregation has a backward
+    (L forward + L backward calls per epoch)."""
+
+    def vertexForward(self, a, x, layer):
+        """GCN_EAGER_single.hpp:201-212: layer 0 = W0 x; deeper layers = W_l relu(dropout(a))."""
+        if layer == 0:
+            return self.P[layer].forward(a)
+        if self.drop_rate > 0:
+            a = torch.nn.functional.dropout(a, self.drop_rate, training=True)
+        return self.P[layer].forward(torch.relu(a))
+
+    def Forward(self):
+        """GCN_EAGER_single.hpp:214-227."""
+        for i in range(len(self.layers) - 1):
+            y_i = self.ctx.runVertexForward(lambda n, v, _l=i: self.vertexForward(n, v, _l), self.X[i], self.X[i])
+            self.X[i + 1] = self.ctx.runGraphOp(self.op_class, self.pg, None, y_i.contiguous(), **self.op_kwargs)
+
+    def Loss(self):
+        """GCN_EAGER_single.hpp:185-194."""
+        a = self.X[-1].log_softmax(1)
+        self.loss = torch.nn.functional.nll_loss(a.index_select(0, self.train_rows),
+                                                 self.L_GT.index_select(0, self.train_rows))
+        self.ctx.appendNNOp(self.X[-1], self.loss)
+
+
 class GATImpl:
     """Multi-head GAT on the fused aggregation path - the flow of toolkits/GAT_CPU_DIST_OPTM.hpp:196-241 (per-vertex
     attention scores -> [E, H] edge logits -> edge softmax -> DistAggregateDstFuseWeight) on the GPU operators, with
