@@ -199,6 +199,21 @@ int nts_gat_fused_aggregate_backward(float *mirror_grad, float *src_score_grad, 
                                      const nts_vid_t *column_offset, const nts_vid_t *mirror_index,
                                      nts_vid_t batch_size, nts_vid_t feature_size, nts_vid_t heads,
                                      float negative_slope, void *stream);
+/* Same results without per-edge atomics: a destination-major pass over the CSC (dst_score_grad) and a source-major
+ * pass over the CSR of the same edges keyed by MIRROR SLOT (mirror_grad, src_score_grad), both with register
+ * accumulators.  slot_row_offset[mirror_size+1] / slot_column_indices[E] (local destination ids) list the out-edges
+ * of every mirror slot; dst_pack is a 16-byte-aligned workspace of batch_size*heads*4 floats.  Shapes the passes do
+ * not cover (heads > 1 with a non-power-of-two head width in vectors, rows wider than 128 vectors) fall back to
+ * nts_gat_fused_aggregate_backward.  The three gradient outputs must be zeroed by the caller. */
+int nts_gat_fused_aggregate_backward_two_pass(float *mirror_grad, float *src_score_grad, float *dst_score_grad,
+                                              float *dst_pack, const float *mirror, const float *src_score,
+                                              const float *dst_score, const float *seg_max, const float *seg_sum,
+                                              const float *out_dot_grad, const float *dst_grad,
+                                              const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                              const nts_vid_t *mirror_index, const nts_vid_t *slot_row_offset,
+                                              const nts_vid_t *slot_column_indices, nts_vid_t batch_size,
+                                              nts_vid_t mirror_size, nts_vid_t feature_size, nts_vid_t heads,
+                                              float negative_slope, void *stream);
 
 /* ---- (vid,row) message records: the reference's host-staged exchange format (comm/network.h:143-149) ---
  * record k = { uint32 vid; float row[feature_size]; }, read through mapped pinned host memory. */

@@ -44,6 +44,9 @@ __device__ __forceinline__ float vec_dot(float4 a, float4 b) {
 __device__ __forceinline__ float vec_scale(float a, float s) { return a * s; }
 __device__ __forceinline__ float2 vec_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 __device__ __forceinline__ float4 vec_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ void vec_zero(float &a) { a = 0.f; }
+__device__ __forceinline__ void vec_zero(float2 &a) { a = make_float2(0.f, 0.f); }
+__device__ __forceinline__ void vec_zero(float4 &a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float vec_add(float a, float b) { return a + b; }
 __device__ __forceinline__ float2 vec_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float4 vec_add(float4 a, float4 b) {
@@ -666,6 +669,176 @@ __global__ void __launch_bounds__(kThreads)
   } // quantum loop
 }
 
+// ---- K7 backward without per-edge atomics: one destination-major and one source-major pass -------------------------
+// The single-pass kernels above are destination-major, so every edge issues a vector `red` into its SOURCE's gradient
+// row and a scalar atomic into its source's score gradient; on a power-law graph those collide on hub sources.  The two
+// passes below walk the same edges twice, each time in the order in which ITS outputs are segment sums, so both keep
+// register accumulators and write once per row (plain read-modify-write when the row lies inside the warp's edge
+// quantum, `red`/atomicAdd only for rows cut by a quantum boundary):
+//   destination-major (CSC): gathers mirror[slot(e)] and src_score[slot(e)], row constants g[dst], pack[dst]
+//                            -> dst_score_grad[dst,h] = sum_e d_pre(e,h)
+//   source-major (CSR):      gathers g[dst(e)] and pack[dst(e)], row constants mirror[slot], src_score[slot]
+//                            -> mirror_grad[slot] = sum_e a(e,h) g[dst(e)],  src_score_grad[slot,h] = sum_e d_pre(e,h)
+// pack[v,h] = { dst_score, seg_max + log(seg_sum), <out[v,h], g[v,h]>, 0 } so that one 16-byte load carries everything
+// an edge needs about its destination:  a = exp(leaky(s + d) - lse),  d_pre = a (dot - <out,g>) leaky'(s + d).
+constexpr uint32_t kBwdQuantum = 256;
+
+__global__ void __launch_bounds__(kThreads)
+    gat_pack_dst_kernel(float4 *__restrict__ pack, const float *__restrict__ d_att, const float *__restrict__ seg_max,
+                        const float *__restrict__ seg_sum, const float *__restrict__ out_dot_g, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    pack[i] = make_float4(__ldg(d_att + i), __ldg(seg_max + i) + logf(__ldg(seg_sum + i)), __ldg(out_dot_g + i), 0.f);
+}
+
+// VEC floats per lane load, KB chunks of 32 vectors per row, U edges gathered before any arithmetic.
+// ONEHEAD: heads == 1, any row width (the dot product is a full-warp sum); otherwise a head is a power-of-two number
+// of vectors <= 32 and per-head dots are segmented xor-shuffle sums (lanes of one head are contiguous).
+template <int VEC, int KB, int U, bool SRC_MAJOR, bool ONEHEAD>
+__global__ void __launch_bounds__(kThreads)
+    gat_backward_pass_kernel(float *__restrict__ vec_out, float *__restrict__ score_out,
+                             const float *__restrict__ gathered, const float *__restrict__ row_vals,
+                             const float *__restrict__ src_score, const float4 *__restrict__ dst_pack,
+                             const uint32_t *__restrict__ col, const uint32_t *__restrict__ off,
+                             const uint32_t *__restrict__ col_map, uint32_t n_rows, uint32_t F, uint32_t H,
+                             float slope) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nvec = F / VEC;
+  const uint32_t head_vecs = ONEHEAD ? 32u : nvec / H;
+  uint32_t hk[KB];
+  bool act[KB], lead[KB];
+#pragma unroll
+  for (int k = 0; k < KB; k++) {
+    act[k] = lane + 32 * k < nvec;
+    hk[k] = (ONEHEAD || !act[k]) ? 0u : (lane + 32 * k) / head_vecs;
+    lead[k] = ONEHEAD ? (lane == 0 && k == 0) : (act[k] && (lane % head_vecs) == 0);
+  }
+  const uint32_t n_edges = __ldg(off + n_rows);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kBwdQuantum < n_edges; qw += nwarps) {
+    const uint32_t e0 = (uint32_t)(qw * kBwdQuantum);
+    const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kBwdQuantum);
+    uint32_t row = eo_find_row(off, n_rows, e0);
+    uint32_t row_begin = __ldg(off + row), row_end = __ldg(off + row + 1);
+    V yv[KB], mg[KB];
+    float rs[KB], acc[KB];
+    float4 rp[KB];
+    auto load_row = [&]() {
+      const V *yr = reinterpret_cast<const V *>(row_vals + (size_t)row * F);
+#pragma unroll
+      for (int k = 0; k < KB; k++) {
+        acc[k] = 0.f;
+        if (act[k])
+          yv[k] = __ldg(yr + lane + 32 * k);
+        if constexpr (SRC_MAJOR) {
+          rs[k] = __ldg(src_score + (size_t)row * H + hk[k]);
+          vec_zero(mg[k]);
+        } else {
+          rp[k] = __ldg(dst_pack + (size_t)row * H + hk[k]);
+        }
+      }
+    };
+    auto flush_row = [&]() {
+      const bool whole = row_begin >= e0 && row_end <= e1; // no other warp touches this row
+#pragma unroll
+      for (int k = 0; k < KB; k++) {
+        if constexpr (SRC_MAJOR) {
+          if (act[k]) {
+            V *o = reinterpret_cast<V *>(vec_out + (size_t)row * F) + lane + 32 * k;
+            if (whole)
+              *o = vec_add(*o, mg[k]);
+            else
+              vec_red_add<VEC>(o, mg[k]);
+          }
+        }
+        if (lead[k]) {
+          float *o = score_out + (size_t)row * H + hk[k];
+          if (whole)
+            *o += acc[k];
+          else if (acc[k] != 0.f)
+            atomicAdd(o, acc[k]);
+        }
+      }
+    };
+    load_row();
+    for (uint32_t eb = e0; eb < e1; eb += 32) {
+      const uint32_t cnt = min(32u, e1 - eb);
+      uint32_t my_idx = 0;
+      if (lane < cnt) {
+        my_idx = __ldg(col + eb + lane);
+        if (col_map)
+          my_idx = __ldg(col_map + my_idx);
+      }
+      for (uint32_t j = 0; j < cnt; j += U) {
+        V xv[U][KB];
+        float es[U][KB];
+        float4 ep[U][KB];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t idx = __shfl_sync(0xffffffffu, my_idx, min(j + u, cnt - 1));
+          const V *xr = reinterpret_cast<const V *>(gathered + (size_t)idx * F);
+#pragma unroll
+          for (int k = 0; k < KB; k++) {
+            if (act[k])
+              xv[u][k] = __ldg(xr + lane + 32 * k);
+            if constexpr (SRC_MAJOR)
+              ep[u][k] = __ldg(dst_pack + (size_t)idx * H + hk[k]);
+            else
+              es[u][k] = __ldg(src_score + (size_t)idx * H + hk[k]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t e = eb + j + u;
+          if (e >= e1)
+            break;
+          if (e >= row_end) {
+            flush_row();
+            do {
+              row++;
+              row_begin = row_end;
+              row_end = __ldg(off + row + 1);
+            } while (e >= row_end);
+            load_row();
+          }
+          float dotk[KB];
+#pragma unroll
+          for (int k = 0; k < KB; k++)
+            dotk[k] = act[k] ? vec_dot(xv[u][k], yv[k]) : 0.f;
+          if constexpr (ONEHEAD) {
+            float t = dotk[0];
+#pragma unroll
+            for (int k = 1; k < KB; k++)
+              t += dotk[k];
+            t = warp_sum(t);
+#pragma unroll
+            for (int k = 0; k < KB; k++)
+              dotk[k] = t;
+          } else {
+#pragma unroll
+            for (int k = 0; k < KB; k++)
+              for (uint32_t o = head_vecs >> 1; o > 0; o >>= 1)
+                dotk[k] += __shfl_xor_sync(0xffffffffu, dotk[k], o);
+          }
+#pragma unroll
+          for (int k = 0; k < KB; k++) {
+            const float sc = SRC_MAJOR ? rs[k] : es[u][k];
+            const float4 pk = SRC_MAJOR ? ep[u][k] : rp[k];
+            const float pre = sc + pk.x;
+            const float a = expf(leaky(pre, slope) - pk.y);
+            if constexpr (SRC_MAJOR) {
+              if (act[k])
+                mg[k] = vec_add(mg[k], vec_scale(xv[u][k], a));
+            }
+            acc[k] += a * (dotk[k] - pk.z) * (pre > 0.f ? 1.f : slope);
+          }
+        }
+      }
+    }
+    flush_row();
+  } // quantum loop
+}
+
 // ---- (vid,row) records read from mapped pinned host memory ---------------------------------------------------
 template <bool ACCUM>
 __global__ void __launch_bounds__(kThreads)
@@ -1010,6 +1183,81 @@ int nts_gat_fused_aggregate_backward(float *mirror_grad, float *src_score_grad, 
   else
     NTS_GATB(1);
 #undef NTS_GATB
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+int nts_gat_fused_aggregate_backward_two_pass(float *mirror_grad, float *src_score_grad, float *dst_score_grad,
+                                              float *dst_pack, const float *mirror, const float *src_score,
+                                              const float *dst_score, const float *seg_max, const float *seg_sum,
+                                              const float *out_dot_grad, const float *dst_grad,
+                                              const nts_vid_t *row_indices, const nts_vid_t *column_offset,
+                                              const nts_vid_t *mirror_index, const nts_vid_t *slot_row_offset,
+                                              const nts_vid_t *slot_column_indices, nts_vid_t batch_size,
+                                              nts_vid_t mirror_size, nts_vid_t feature_size, nts_vid_t heads,
+                                              float negative_slope, void *stream) {
+  cudaStream_t st = as_stream(stream);
+  if (batch_size == 0 || feature_size == 0 || mirror_size == 0)
+    return 0;
+  NTS_ARG_CHECK(mirror_grad && src_score_grad && dst_score_grad && dst_pack && mirror && src_score && dst_score &&
+                    seg_max && seg_sum && out_dot_grad && dst_grad && row_indices && column_offset && mirror_index &&
+                    slot_row_offset && slot_column_indices,
+                "null pointer passed to fused GAT backward (two pass)");
+  NTS_ARG_CHECK(heads >= 1 && feature_size % heads == 0, "feature_size must be a multiple of heads");
+  NTS_ARG_CHECK((reinterpret_cast<uintptr_t>(dst_pack) & 15) == 0, "dst_pack must be 16-byte aligned");
+  int vec = pick_vec(feature_size, mirror_grad, mirror, dst_grad);
+  while (vec > 1 && (feature_size / heads) % vec != 0)
+    vec >>= 1;
+  while (vec > 1 && feature_size / vec < 32) // keep all 32 lanes busy on narrow rows
+    vec >>= 1;
+  const uint32_t nvec = feature_size / vec, hv = nvec / heads;
+  const uint32_t kb = (nvec + 31) / 32;
+  const bool one = heads == 1;
+  const bool pow2 = hv >= 1 && (hv & (hv - 1)) == 0 && hv <= 32;
+  if (kb > 4 || !(one || pow2)) // shapes the register-accumulator passes do not cover: single pass with atomics
+    return nts_gat_fused_aggregate_backward(mirror_grad, src_score_grad, dst_score_grad, mirror, src_score, dst_score,
+                                            seg_max, seg_sum, out_dot_grad, dst_grad, row_indices, column_offset,
+                                            mirror_index, batch_size, feature_size, heads, negative_slope, stream);
+  const uint64_t n_pack = (uint64_t)batch_size * heads;
+  gat_pack_dst_kernel<<<stream_grid((n_pack + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+      reinterpret_cast<float4 *>(dst_pack), dst_score, seg_max, seg_sum, out_dot_grad, n_pack);
+  NTS_LAUNCH_CHECK();
+  const unsigned grid = full_grid();
+  const float4 *pk = reinterpret_cast<const float4 *>(dst_pack);
+#define NTS_GAT2(V_, K_, U_, ONE_)                                                                                   \
+  do {                                                                                                               \
+    gat_backward_pass_kernel<V_, K_, U_, false, ONE_><<<grid, kThreads, 0, st>>>(                                    \
+        nullptr, dst_score_grad, mirror, dst_grad, src_score, pk, row_indices, column_offset, mirror_index,          \
+        batch_size, feature_size, heads, negative_slope);                                                            \
+    gat_backward_pass_kernel<V_, K_, U_, true, ONE_><<<grid, kThreads, 0, st>>>(                                     \
+        mirror_grad, src_score_grad, dst_grad, mirror, src_score, pk, slot_column_indices, slot_row_offset, nullptr, \
+        mirror_size, feature_size, heads, negative_slope);                                                           \
+  } while (0)
+#define NTS_GAT2_K(V_, ONE_)                                                                                         \
+  do {                                                                                                               \
+    if (kb == 1)                                                                                                     \
+      NTS_GAT2(V_, 1, 4, ONE_);                                                                                      \
+    else if (kb == 2)                                                                                                \
+      NTS_GAT2(V_, 2, 2, ONE_);                                                                                      \
+    else                                                                                                             \
+      NTS_GAT2(V_, 4, 1, ONE_);                                                                                      \
+  } while (0)
+#define NTS_GAT2_V(ONE_)                                                                                             \
+  do {                                                                                                               \
+    if (vec == 4)                                                                                                    \
+      NTS_GAT2_K(4, ONE_);                                                                                           \
+    else if (vec == 2)                                                                                               \
+      NTS_GAT2_K(2, ONE_);                                                                                           \
+    else                                                                                                             \
+      NTS_GAT2_K(1, ONE_);                                                                                           \
+  } while (0)
+  if (one)
+    NTS_GAT2_V(true);
+  else
+    NTS_GAT2_V(false);
+#undef NTS_GAT2_V
+#undef NTS_GAT2_K
+#undef NTS_GAT2
   NTS_LAUNCH_CHECK();
   return 0;
 }

@@ -305,7 +305,7 @@ class DistGPUAggregateDstFuseWeight(_EdgeOp):
 
 
 class DistGPUFusedGATOp(_EdgeOp):
-    """K7: the whole attention + aggregation of one GAT layer in two kernels forward and one backward, never
+    """K7: the whole attention + aggregation of one GAT layer in two kernels forward and two passes backward, never
     materialising an edge-sized tensor (toolkits/GAT_CPU_DIST_OPTM.hpp:196-241 keeps [E,1] logits / attention;
     toolkits/GAT_GPU_DIST.hpp:187-219 keeps four [E,F] messages).
 
@@ -315,10 +315,29 @@ class DistGPUFusedGATOp(_EdgeOp):
         backward(grad_out) -> (d_mirror, d_src_score, d_dst_score)
     """
 
-    def __init__(self, partitioned_graph, active=None, negative_slope=0.2):
+    def __init__(self, partitioned_graph, active=None, negative_slope=0.2, two_pass_backward=True):
         super().__init__(partitioned_graph, active)
         self.slope = float(negative_slope)
+        self.two_pass_backward = bool(two_pass_backward)
         self._saved = None
+
+    @staticmethod
+    def slot_csr(pg):
+        """Out-edges of every mirror slot: (slot_row_offset [M+1], slot_column_indices [E], local destination ids) -
+        the CSR twin of the whole-partition CSC, built once per PartitionedGraph on the device and cached on it."""
+        cached = getattr(pg, "_slot_csr_gpu", None)
+        if cached is not None:
+            return cached
+        col = pg.column_offset_gpu.long()
+        V, M = pg.owned_vertices, pg.owned_mirrors
+        slot = pg.mirror_index_gpu.long()[pg.row_indices_gpu.long()]
+        dst = torch.repeat_interleave(torch.arange(V, device=col.device), col[1:V + 1] - col[:V])
+        order = torch.sort(slot, stable=True).indices
+        csr_dst = dst[order].to(torch.int32).contiguous()
+        off = torch.zeros(M + 1, dtype=torch.int64, device=col.device)
+        off[1:] = torch.cumsum(torch.bincount(slot, minlength=M), 0)
+        pg._slot_csr_gpu = (off.to(torch.int32).contiguous(), csr_dst)
+        return pg._slot_csr_gpu
 
     def forward(self, mirror, src_score, dst_score):
         pg = self._topo()
@@ -348,6 +367,16 @@ class DistGPUFusedGATOp(_EdgeOp):
         dm = torch.zeros_like(x)
         ds = torch.zeros_like(s)
         dd = torch.zeros_like(d)
+        if self.two_pass_backward:
+            # no per-edge atomics: a destination-major and a source-major pass, each with register accumulators
+            slot_off, slot_dst = self.slot_csr(pg)
+            pack = torch.empty((pg.owned_vertices, H, 4), dtype=torch.float32, device=x.device)
+            _lib.call("nts_gat_fused_aggregate_backward_two_pass", _ptr(dm), _ptr(ds), _ptr(dd), _ptr(pack), _ptr(x),
+                      _ptr(s), _ptr(d), _ptr(seg_max), _ptr(seg_sum), _ptr(out_dot_g), _ptr(g),
+                      _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu),
+                      _ptr(slot_off), _ptr(slot_dst), pg.owned_vertices, x.shape[0], x.shape[1], H, self.slope,
+                      _stream())
+            return dm, ds, dd
         _lib.call("nts_gat_fused_aggregate_backward", _ptr(dm), _ptr(ds), _ptr(dd), _ptr(x), _ptr(s), _ptr(d),
                   _ptr(seg_max), _ptr(seg_sum), _ptr(out_dot_g), _ptr(g), _ptr(pg.row_indices_gpu),
                   _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, x.shape[1], H,

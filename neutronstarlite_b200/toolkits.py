@@ -197,9 +197,11 @@ class GATImpl:
     message; the only edge-sized tensors are [E, H]."""
 
     def __init__(self, partitioned_graph, layers, features, labels, mask, heads=8, learn_rate=0.01,
-                 weight_decay=0.0001, exchange=None, seed=0, sum_fanout_grads=True, fused_kernel=False):
+                 weight_decay=0.0001, exchange=None, seed=0, sum_fanout_grads=True, fused_kernel=False,
+                 two_pass_backward=True):
         self.pg = partitioned_graph
         self.fused_kernel = fused_kernel  # True: K7 (ops.DistGPUFusedGATOp), no edge-sized tensors at all
+        self.two_pass_backward = two_pass_backward
         self.layers = list(layers)
         self.device = features.device
         self.heads = [heads] * (len(self.layers) - 2) + [1]
@@ -244,7 +246,8 @@ class GATImpl:
             dst_att = ctx.runVertexForward(
                 lambda x, _i=i: (x.view(-1, H, D) * self.ar[_i].W).sum(-1).contiguous(), X_trans)
             if self.fused_kernel:
-                nbr = ctx.runGraphOpN(ops.DistGPUFusedGATOp, pg, None, [mirror, src_att, dst_att])
+                nbr = ctx.runGraphOpN(ops.DistGPUFusedGATOp, pg, None, [mirror, src_att, dst_att],
+                                      two_pass_backward=self.two_pass_backward)
             else:
                 e_src = ctx.runGraphOp(ops.DistGPUScatterSrc, pg, None, src_att)
                 e_dst = ctx.runGraphOp(ops.DistGPUScatterDst, pg, None, dst_att)

@@ -43,23 +43,61 @@ DROP_RATE:0.0
 """
 
 
-def run(binary, algo, epochs, layers="1433-128-7", timeout=600):
+def _run_ranks(binary, cfg, nprocs, env, timeout):
+    """rank 0's output and the first non-zero exit status of `nprocs` ranks under the MPI stand-in
+    (oracle/shim/mpi.h: NTS_SHIM_SIZE / NTS_SHIM_RANK / NTS_SHIM_DIR).  The reference never calls cudaSetDevice
+    (device 0 always), so rank r is pinned to GPU r % n_gpus through CUDA_VISIBLE_DEVICES; with one GPU all ranks
+    share it - the host-side exchange of the reference does not care."""
+    if nprocs == 1:
+        p = subprocess.run([binary, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
+                           timeout=timeout)
+        return p.stdout, p.returncode
+    import shutil
+    try:
+        import torch
+        n_gpus = max(1, torch.cuda.device_count())
+    except Exception:
+        n_gpus = 1
+    scratch = tempfile.mkdtemp(prefix="nts_shim_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    procs = []
+    try:
+        for r in range(nprocs):
+            e = dict(env, NTS_SHIM_SIZE=str(nprocs), NTS_SHIM_RANK=str(r), NTS_SHIM_DIR=scratch,
+                     CUDA_VISIBLE_DEVICES=str(r % n_gpus))
+            procs.append(subprocess.Popen([binary, cfg], env=e, text=True,
+                                          stdout=subprocess.PIPE if r == 0 else subprocess.DEVNULL,
+                                          stderr=subprocess.STDOUT if r == 0 else subprocess.DEVNULL))
+        out, _ = procs[0].communicate(timeout=timeout)
+        rc = procs[0].returncode
+        for q in procs[1:]:
+            q.wait(timeout=60)
+            rc = rc or q.returncode
+        return out, rc
+    finally:
+        for q in procs:
+            if q.poll() is None:
+                q.kill()
+        shutil.rmtree(scratch, ignore_errors=True)
+
+
+def run(binary, algo, epochs, layers="1433-128-7", timeout=600, nprocs=1):
     with tempfile.TemporaryDirectory() as d:
         cfg = os.path.join(d, "c.cfg")
         open(cfg, "w").write(CFG.format(algo=algo, layers=layers, epochs=epochs, data=os.path.join(REF, "data")))
         env = dict(os.environ)
         env.setdefault("NTS_THREADS", "8")
         env["OMP_NUM_THREADS"] = env["NTS_THREADS"]
-        p = subprocess.run([binary, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
-                           timeout=timeout)
-    out = p.stdout
+        out, rc = _run_ranks(binary, cfg, nprocs, env, timeout)
+
+    class p:   # keep the field names used below
+        returncode = rc
     losses = [float(x) for x in re.findall(r"Epoch\[\d+\]:loss\s+([-0-9.eE+]+)", out)]
     accs = re.findall(r"(Train|Eval|Test)\s+ACC:\s+([0-9.]+)", out)
     last = {}
     for k, v in accs:
         last[k.lower()] = float(v)
     passed = re.findall(r"(\d+) is passed|passed", out)
-    return {"algo": algo, "rc": p.returncode, "epochs": len(losses), "loss_first": losses[0] if losses else None,
+    return {"algo": algo, "ranks": nprocs, "rc": p.returncode, "epochs": len(losses), "loss_first": losses[0] if losses else None,
             "loss_last": losses[-1] if losses else None, "acc": last, "tail": out[-600:] if p.returncode else "",
             "raw_passed_lines": [ln for ln in out.splitlines() if "pass" in ln.lower()][:12]}
 
@@ -140,6 +178,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=30)
     ap.add_argument("--algos", default="GCNEAGERSINGLE,GCN,GATGPUDIST,test_getdep")
+    ap.add_argument("-np", type=int, default=1, help="ranks of the reference's host code (MPI stand-in); P > 1 runs "
+                    "its sync_compute_decoupled / compute_sync_decoupled exchange on top of our kernels")
     ap.add_argument("--synthetic", type=int, default=0, metavar="DIV",
                     help="compare ours vs the reference's own kernels through the reference's host code on 1/DIV of "
                          "the Reddit-shaped graph")
@@ -149,10 +189,10 @@ def main():
     res = {}
     cpu = os.path.join(REF, "nts_ref_main")
     gpu = os.path.join(REF, "nts_dropin_main")
-    res["cpu_reference_GCNCPU"] = run(cpu, "GCNCPU", a.epochs)
+    res["cpu_reference_GCNCPU"] = run(cpu, "GCNCPU", a.epochs, nprocs=a.np)
     for algo in a.algos.split(","):
         try:
-            res["dropin_" + algo] = run(gpu, algo, a.epochs)
+            res["dropin_" + algo] = run(gpu, algo, a.epochs, nprocs=a.np)
         except subprocess.TimeoutExpired:
             res["dropin_" + algo] = {"algo": algo, "rc": "timeout"}
     print(json.dumps(res, indent=1))

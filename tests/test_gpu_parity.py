@@ -448,8 +448,9 @@ def test_offsets_beyond_32_bits():
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("H,D", [(8, 8), (8, 64), (1, 64), (3, 5), (2, 16), (1, 41), (16, 4)])
-def test_fully_fused_gat_layer_vs_operator_chain(H, D):
+@pytest.mark.parametrize("two_pass", [True, False])
+@pytest.mark.parametrize("H,D", [(8, 8), (8, 64), (1, 64), (3, 5), (2, 16), (1, 41), (16, 4), (1, 200), (4, 32)])
+def test_fully_fused_gat_layer_vs_operator_chain(H, D, two_pass):
     """K7 (stats + attention-weighted aggregation + single-pass backward) against the chain of individually tested
     operators (scatter-src / scatter-dst / leaky-relu / edge-softmax / fused aggregation) on a graph with a hub
     segment longer than the block-cooperative threshold."""
@@ -484,7 +485,7 @@ def test_fully_fused_gat_layer_vs_operator_chain(H, D):
     ds_ref = sc_s.backward(d_pre.contiguous())
     dd_ref = sc_d.backward(d_pre.contiguous())
     # K7
-    fused = ops.DistGPUFusedGATOp(pg, negative_slope=0.2)
+    fused = ops.DistGPUFusedGATOp(pg, negative_slope=0.2, two_pass_backward=two_pass)
     out = fused.forward(mirror, s_att, d_att)
     dm, ds, dd = fused.backward(g)
     torch.cuda.synchronize()

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--fused-kernel", type=int, default=1, help="1: K7 DistGPUFusedGATOp, 0: [E,H] operator chain")
+    ap.add_argument("--two-pass", type=int, default=1, help="K7 backward: 1 = dst-major + src-major passes without "
+                    "per-edge atomics, 0 = single destination-major pass with atomics")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     V, E_rand, _ = synth.WORKLOADS[a.workload]
@@ -47,7 +49,7 @@ def main():
     torch.cuda.empty_cache()
     feats, labels, mask = synth.features_labels_mask(V, layers[0], layers[-1], dev)
     model = GATImpl(pg, layers, feats, labels, mask, heads=a.heads, exchange=GpuExchange(pg),
-                    fused_kernel=bool(a.fused_kernel))
+                    fused_kernel=bool(a.fused_kernel), two_pass_backward=bool(a.two_pass))
     for _ in range(a.warmup):
         model.run_epoch()
     torch.cuda.synchronize()
