@@ -376,7 +376,7 @@ def main():
             b = k & 1
             cur = torch.cuda.current_stream()
             cur.wait_event(ready[b])
-            model.X[0] = dev_in[b].requires_grad_(True)
+            model.X[0] = dev_in[b] if eager else dev_in[b].requires_grad_(True)
             prefetch(k + 1)
             loss, _ = model.run_epoch()
             consumed[b].record(cur)
@@ -420,7 +420,8 @@ def main():
         achieved = b_alg / (k["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "segment_gather_sum_kernel (fwd, F=%d)" % F0, "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                "traffic": _ncu_traffic() if (args.workload == "reddit" and world == 1 and args.zipf_s == 1.0) else None,
+                "traffic": _ncu_traffic() if (args.workload == "reddit" and world == 1 and args.zipf_s == 1.0
+                                              and not eager) else None,
                 "launches": k["calls"], "avg_ms_per_launch": k["ms"] / k["calls"],
                 "algorithmic_bytes_per_launch": b_alg / k["calls"]}
     kernels = {"%s_F%d" % (tag, F): {"calls": d["calls"], "avg_ms": d["ms"] / d["calls"],

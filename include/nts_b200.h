@@ -176,7 +176,8 @@ int nts_aggregate_dst_fuse_weight_backward_heads(float *mirror_grad, float *edge
 /* ---- fully fused GAT layer (K7): edge logits / attention are never materialised ---------------------------------
  * The flow of toolkits/GAT_CPU_DIST_OPTM.hpp:196-241 (per-vertex scores -> leaky_relu -> edge softmax ->
  * DistAggregateDstFuseWeight) with a[e,h] = softmax_seg(leaky_relu(src_score[slot(e),h] + dst_score[dst(e),h]))
- * recomputed inside the kernels; slot(e) = mirror_index[row_indices[e]], head h owns columns [h*D,(h+1)*D), D <= 512.
+ * recomputed inside the kernels; slot(e) = mirror_index[row_indices[e]] (or row_indices[e] itself when mirror_index
+ * is NULL, i.e. the caller has applied the lookup once), head h owns columns [h*D,(h+1)*D), D <= 512.
  *   stats    : seg_max[d,h], seg_sum[d,h]                                   ([batch_size, heads] each)
  *   forward  : output[d, hD+c] += sum_e a[e,h] * mirror[slot(e), hD+c]
  *   backward : mirror_grad[slot,hD+c] += a*g[d,hD+c];  src_score_grad[slot,h] += dpre;  dst_score_grad[d,h] += dpre

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
                               const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
                               uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
                               uint32_t tile_major, uint32_t heads, AttParams att) {
-  static_assert(!(HM != 0 && BULK), "per-head weights are not bulk-staged");
+  static_assert(!(HM == 1 && BULK), "[E, H] weight matrices are not bulk-staged (indices of HM 0 / 2 are)");
   using V = typename Vec<VEC>::type;
   const uint32_t n_edges = (uint32_t)n_edges64;
   const uint32_t lane = threadIdx.x & 31;
@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
         if constexpr (BULK) {
           uint32_t id = s_idx[e + j + u - cta_e_base];
           s = slot_of ? __ldg(slot_of + id) : id - base;
-          wu[u][0] = w ? s_w[e + j + u - cta_e_base] : 1.f;
+          if constexpr (HM == 0)
+            wu[u][0] = w ? s_w[e + j + u - cta_e_base] : 1.f;
         } else {
           s = __shfl_sync(0xffffffffu, my_src, j + u);
           if constexpr (HM == 0)
@@ -358,7 +359,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
       if constexpr (BULK) {
         uint32_t id = s_idx[e + j - cta_e_base];
         s = slot_of ? __ldg(slot_of + id) : id - base;
-        wj[0] = w ? s_w[e + j - cta_e_base] : 1.f;
+        if constexpr (HM == 0)
+          wj[0] = w ? s_w[e + j - cta_e_base] : 1.f;
       } else {
         s = __shfl_sync(0xffffffffu, my_src, j);
         if constexpr (HM == 0)
@@ -465,7 +467,16 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
   if (att || sh.heads > 1) {
     if constexpr (MINB == 1) { // per-head kernels exist for the untuned occupancy points only
       g_last_smem = 0;
-      if (att)
+      if (att && bulk) { // fused attention with TMA-staged index tiles (no weight array to stage)
+        size_t span_cap = (size_t)kWarpsPerBlock * Q + 8;
+        size_t smem = 16 + 2 * span_cap * 4;
+        auto kern = segment_gather_sum_kernel<VEC, K, U, true, 1, 2>;
+        NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_last_smem = (int)smem;
+        kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, nullptr, idx, off, slot_of, base, n_rows,
+                                                                  n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
+                                                                  sh.heads, *att);
+      } else if (att)
         segment_gather_sum_kernel<VEC, K, U, false, 1, 2><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
             in, out, nullptr, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
             sh.heads, *att);
@@ -513,7 +524,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
     NTS_ARG_CHECK(F % heads == 0, "feature_size must be a multiple of heads");
   }
   LaunchShape s = pick_shape(in, out, F, heads);
-  if (heads > 1 || att) { // per-head kernels: untuned occupancy point, shuffle-broadcast indices
+  if (heads > 1 || att) { // per-head kernels: untuned occupancy point
     s.minb = 1;
     int budget = 40 / (s.k * s.vec);
     s.u = budget >= 8 ? 8 : (budget >= 4 ? 4 : 2);
@@ -527,7 +538,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   }
   Q = (Q + 31u) & ~31u;
   int variant = g_variant == 0 ? 2 : g_variant; // measured on B200: bulk-staged indices are ~15-20% faster
-  bool bulk = variant == 2 && heads <= 1 && !att; // [E, H] / attention weights are not bulk-staged
+  bool bulk = variant == 2 && (att || heads <= 1); // [E, H] weight matrices are not bulk-staged
   // the bulk copies need 16-byte aligned index/weight arrays (cudaMalloc gives 256)
   if (bulk && !(aligned_to(idx, 16) && (!w || aligned_to(w, 16)))) {
     bulk = false;
@@ -606,7 +617,7 @@ int nts_gat_fused_aggregate_forward(const float *mirror, float *output, const fl
                                     const nts_vid_t *mirror_index, nts_vid_t batch_size, uint64_t n_edges,
                                     nts_vid_t feature_size, nts_vid_t heads, float negative_slope, void *stream) {
   NTS_ARG_CHECK(heads >= 1 && feature_size % heads == 0, "feature_size must be a multiple of heads");
-  NTS_ARG_CHECK(src_score && dst_score && seg_max && seg_sum && mirror_index, "null pointer passed to fused GAT forward");
+  NTS_ARG_CHECK(src_score && dst_score && seg_max && seg_sum, "null pointer passed to fused GAT forward");
   nts::AttParams att = {src_score, dst_score, seg_max, seg_sum, negative_slope};
   return nts::segment_gather_sum(mirror, output, nullptr, row_indices, column_offset, mirror_index, 0, batch_size,
                                  n_edges, feature_size, nts::as_stream(stream), heads, &att);

@@ -27,6 +27,13 @@ __device__ __forceinline__ uint32_t eo_find_row(const uint32_t *__restrict__ off
   return lo;
 }
 
+// mirror slot of edge e: through the MirrorIndex table, or directly when the index array already holds slots
+__device__ __forceinline__ uint32_t slot_at(const uint32_t *__restrict__ row_idx,
+                                            const uint32_t *__restrict__ mirror_index, size_t e) {
+  const uint32_t id = __ldg(row_idx + e);
+  return mirror_index ? __ldg(mirror_index + id) : id;
+}
+
 template <int VEC> __device__ __forceinline__ void vec_red_add(typename Vec<VEC>::type *p, typename Vec<VEC>::type a);
 template <> __device__ __forceinline__ void vec_red_add<1>(float *p, float a) { atomicAdd(p, a); }
 template <> __device__ __forceinline__ void vec_red_add<2>(float2 *p, float2 a) {
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(kThreads)
         row++;
         row_end = __ldg(off + row + 1);
       }
-      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
+      const uint32_t slot = slot_at(row_idx, mirror_index, e);
       const V *gm = reinterpret_cast<const V *>(g + (size_t)row * F);
       const V *mm = reinterpret_cast<const V *>(mirror + (size_t)slot * F);
       V *dm = reinterpret_cast<V *>(mirror_grad + (size_t)slot * F);
@@ -341,13 +348,13 @@ __global__ void __launch_bounds__(kThreads)
       const float dv = __ldg(d_att + (size_t)r * H + h);
       float mx = -INFINITY;
       for (uint32_t i = tid; i < deg; i += nthr) {
-        const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+        const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
         mx = fmaxf(mx, leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope));
       }
       mx = hub ? block_reduce<true>(mx, scratch) : warp_max(mx);
       float sum = 0.f;
       for (uint32_t i = tid; i < deg; i += nthr) {
-        const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+        const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
         sum += expf(leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope) - mx);
       }
       sum = hub ? block_reduce<false>(sum, scratch) : warp_sum(sum);
@@ -406,13 +413,13 @@ __global__ void __launch_bounds__(kThreads)
     const float dv = __ldg(d_att + (size_t)r * H + h);
     float mx = -INFINITY;
     for (uint32_t i = first; i < deg; i += step) {
-      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+      const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
       mx = fmaxf(mx, leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope));
     }
     mx = head_max(mx);
     float sum = 0.f;
     for (uint32_t i = first; i < deg; i += step) {
-      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+      const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
       sum += expf(leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope) - mx);
     }
     sum = head_sum(sum);
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(kThreads)
     const float mx_all = PASS == 1 ? __ldg(seg_max + (size_t)r * H + h) : 0.f;
     float acc = PASS == 0 ? -INFINITY : 0.f;
     for (uint32_t i = lo + wid * kEdgesPerStep + el; i < hi; i += kWarps * kEdgesPerStep) {
-      const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + b + i));
+      const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
       const float x = leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope);
       acc = PASS == 0 ? fmaxf(acc, x) : acc + expf(x - mx_all);
     }
@@ -545,7 +552,7 @@ __global__ void __launch_bounds__(kThreads)
       const uint32_t cnt = min(32u, e1 - eb);
       uint32_t my_slot = 0;
       if (lane < cnt)
-        my_slot = __ldg(mirror_index + __ldg(row_idx + eb + lane));
+        my_slot = slot_at(row_idx, mirror_index, eb + lane);
       V m_next[KB];
       {
         const uint32_t s0 = __shfl_sync(0xffffffffu, my_slot, 0);
@@ -644,7 +651,7 @@ __global__ void __launch_bounds__(kThreads)
             row_end = __ldg(off + row + 1);
           } while (e >= row_end);
         }
-        const uint32_t slot = __ldg(mirror_index + __ldg(row_idx + e));
+        const uint32_t slot = slot_at(row_idx, mirror_index, e);
         const size_t rh = (size_t)row * H + h;
         const float pre = __ldg(s_att + (size_t)slot * H + h) + __ldg(d_att + rh);
         const float a = expf(leaky(pre, slope) - __ldg(seg_max + rh)) / __ldg(seg_sum + rh);
@@ -1083,7 +1090,7 @@ int nts_gat_softmax_stats(float *seg_max, float *seg_sum, const float *src_score
                           nts_vid_t batch_size, nts_vid_t heads, float negative_slope, void *stream) {
   if (batch_size == 0 || heads == 0)
     return 0;
-  NTS_ARG_CHECK(seg_max && seg_sum && src_score && dst_score && row_indices && column_offset && mirror_index,
+  NTS_ARG_CHECK(seg_max && seg_sum && src_score && dst_score && row_indices && column_offset,
                 "null pointer passed to gat_softmax_stats");
   unsigned grid = (batch_size + kRowsPerCta - 1) / kRowsPerCta;
   cudaStream_t st = as_stream(stream);
@@ -1130,7 +1137,7 @@ int nts_gat_fused_aggregate_backward(float *mirror_grad, float *src_score_grad, 
   if (batch_size == 0 || feature_size == 0)
     return 0;
   NTS_ARG_CHECK(mirror_grad && src_score_grad && dst_score_grad && mirror && src_score && dst_score && seg_max &&
-                    seg_sum && out_dot_grad && dst_grad && row_indices && column_offset && mirror_index,
+                    seg_sum && out_dot_grad && dst_grad && row_indices && column_offset,
                 "null pointer passed to fused GAT backward");
   NTS_ARG_CHECK(heads >= 1 && feature_size % heads == 0, "feature_size must be a multiple of heads");
   int vec = pick_vec(feature_size, mirror_grad, mirror, dst_grad);
@@ -1200,7 +1207,7 @@ int nts_gat_fused_aggregate_backward_two_pass(float *mirror_grad, float *src_sco
   if (batch_size == 0 || feature_size == 0 || mirror_size == 0)
     return 0;
   NTS_ARG_CHECK(mirror_grad && src_score_grad && dst_score_grad && dst_pack && mirror && src_score && dst_score &&
-                    seg_max && seg_sum && out_dot_grad && dst_grad && row_indices && column_offset && mirror_index &&
+                    seg_max && seg_sum && out_dot_grad && dst_grad && row_indices && column_offset &&
                     slot_row_offset && slot_column_indices,
                 "null pointer passed to fused GAT backward (two pass)");
   NTS_ARG_CHECK(heads >= 1 && feature_size % heads == 0, "feature_size must be a multiple of heads");

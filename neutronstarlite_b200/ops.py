@@ -322,6 +322,16 @@ class DistGPUFusedGATOp(_EdgeOp):
         self._saved = None
 
     @staticmethod
+    def slot_indices(pg):
+        """row_indices with the MirrorIndex lookup already applied (mirror slot of every CSC edge), cached on the
+        graph: the kernels then skip one dependent load per edge (the C ABI accepts mirror_index = NULL for this)."""
+        cached = getattr(pg, "_slot_indices_gpu", None)
+        if cached is None:
+            cached = pg.mirror_index_gpu[pg.row_indices_gpu.long()].to(torch.int32).contiguous()
+            pg._slot_indices_gpu = cached
+        return cached
+
+    @staticmethod
     def slot_csr(pg):
         """Out-edges of every mirror slot: (slot_row_offset [M+1], slot_column_indices [E], local destination ids) -
         the CSR twin of the whole-partition CSC, built once per PartitionedGraph on the device and cached on it."""
@@ -330,7 +340,7 @@ class DistGPUFusedGATOp(_EdgeOp):
             return cached
         col = pg.column_offset_gpu.long()
         V, M = pg.owned_vertices, pg.owned_mirrors
-        slot = pg.mirror_index_gpu.long()[pg.row_indices_gpu.long()]
+        slot = DistGPUFusedGATOp.slot_indices(pg).long()
         dst = torch.repeat_interleave(torch.arange(V, device=col.device), col[1:V + 1] - col[:V])
         order = torch.sort(slot, stable=True).indices
         csr_dst = dst[order].to(torch.int32).contiguous()
@@ -347,11 +357,12 @@ class DistGPUFusedGATOp(_EdgeOp):
         H = int(s.shape[1])
         seg_max = torch.empty((pg.owned_vertices, H), dtype=torch.float32, device=x.device)
         seg_sum = torch.empty_like(seg_max)
-        _lib.call("nts_gat_softmax_stats", _ptr(seg_max), _ptr(seg_sum), _ptr(s), _ptr(d), _ptr(pg.row_indices_gpu),
-                  _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu), pg.owned_vertices, H, self.slope, _stream())
+        slots = self.slot_indices(pg)
+        _lib.call("nts_gat_softmax_stats", _ptr(seg_max), _ptr(seg_sum), _ptr(s), _ptr(d), _ptr(slots),
+                  _ptr(pg.column_offset_gpu), 0, pg.owned_vertices, H, self.slope, _stream())
         out = torch.zeros((pg.owned_vertices, x.shape[1]), dtype=torch.float32, device=x.device)
         _lib.call("nts_gat_fused_aggregate_forward", _ptr(x), _ptr(out), _ptr(s), _ptr(d), _ptr(seg_max),
-                  _ptr(seg_sum), _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu),
+                  _ptr(seg_sum), _ptr(slots), _ptr(pg.column_offset_gpu), 0,
                   pg.owned_vertices, pg.owned_edges, x.shape[1], H, self.slope, _stream())
         self._saved = (x, s, d, seg_max, seg_sum, out)
         return out
@@ -373,7 +384,7 @@ class DistGPUFusedGATOp(_EdgeOp):
             pack = torch.empty((pg.owned_vertices, H, 4), dtype=torch.float32, device=x.device)
             _lib.call("nts_gat_fused_aggregate_backward_two_pass", _ptr(dm), _ptr(ds), _ptr(dd), _ptr(pack), _ptr(x),
                       _ptr(s), _ptr(d), _ptr(seg_max), _ptr(seg_sum), _ptr(out_dot_g), _ptr(g),
-                      _ptr(pg.row_indices_gpu), _ptr(pg.column_offset_gpu), _ptr(pg.mirror_index_gpu),
+                      _ptr(self.slot_indices(pg)), _ptr(pg.column_offset_gpu), 0,
                       _ptr(slot_off), _ptr(slot_dst), pg.owned_vertices, x.shape[0], x.shape[1], H, self.slope,
                       _stream())
             return dm, ds, dd

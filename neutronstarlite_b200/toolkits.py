@@ -167,6 +167,12 @@ class GCNEagerImpl(GCNImpl):
     aggregate.  The tape is [NNOP, GRAPHOP, NNOP, GRAPHOP, NNOP(loss)], so every aggregation has a backward
     (L forward + L backward calls per epoch)."""
 
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        # the input features are the input of the first NN op here; nobody reads their gradient, so do not make
+        # autograd compute dX0 = dY0 W0^T (a [V, LAYERS[0]] tensor) every epoch
+        self.X[0] = self.X[0].detach()
+
     def vertexForward(self, a, x, layer):
         """GCN_EAGER_single.hpp:201-212: layer 0 = W0 x; deeper layers = W_l relu(dropout(a))."""
         if layer == 0:
