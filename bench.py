@@ -356,7 +356,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_feats = torch.empty(feats.shape, dtype=torch.float32).pin_memory()
-        host_feats.copy_(feats)
+        host_feats.copy_(feats.detach())      # (a copy from a requires-grad tensor would tie host_feats into autograd)
         host_loss = torch.empty((), dtype=torch.float32).pin_memory()
         # every step copies ITS input from pinned host memory and reads ITS loss back; the copy of step k+1 is
         # issued on a copy stream while step k computes (two device buffers), the way a host-fed trainer would
@@ -367,7 +367,7 @@ def main():
 
         def prefetch(k):
             b = k & 1
-            with torch.cuda.stream(copy_stream):
+            with torch.no_grad(), torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[b])          # the step that used this buffer has finished with it
                 dev_in[b].copy_(host_feats, non_blocking=True)
                 ready[b].record(copy_stream)

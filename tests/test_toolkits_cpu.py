@@ -227,3 +227,24 @@ def test_reference_tape_drops_the_fanout_gradient(fake_ops):
         model.ctx.self_backward(True)
         grads.append(model.P[0].W.grad.clone())
     assert not torch.allclose(grads[0], grads[1])
+
+
+@pytest.mark.parametrize("eager", [False, True])
+def test_input_buffer_can_be_swapped_between_epochs(fake_ops, eager):
+    """A host-fed trainer alternates two input buffers (bench.py's end-to-end leg): same losses as a resident input."""
+    import time
+    from neutronstarlite_b200.toolkits import GCNEagerImpl, GCNImpl
+    G = fake_ops
+    layers = [19, 8, 4]
+    feats, labels, mask = _data(G.V, layers[0], layers[-1])
+    cls = GCNEagerImpl if eager else GCNImpl
+    a = cls(G.pg, layers, feats.clone(), labels, mask, drop_rate=0.0, op_class=ops.ForwardSingleGPUfuseOp)
+    b = cls(G.pg, layers, feats.clone(), labels, mask, drop_rate=0.0, op_class=ops.ForwardSingleGPUfuseOp)
+    bufs = [feats.clone(), feats.clone()]
+    t0 = time.perf_counter()
+    for k in range(4):
+        b.X[0] = bufs[k & 1] if eager else bufs[k & 1].requires_grad_(True)
+        la, _ = a.run_epoch()
+        lb, _ = b.run_epoch()
+        torch.testing.assert_close(la, lb)
+    assert time.perf_counter() - t0 < 20
