@@ -430,21 +430,113 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  // IEEE-754 order trick: non-negative floats order like signed ints, negative floats inversely like unsigned ints;
+  // one `red` instead of a CAS loop (v + 0.f turns -0.0 into +0.0, NaN never reaches here)
+  v += 0.f;
+  if (v >= 0.f)
+    atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// Edge-balanced statistics (H divides 32): a warp owns a quantum of consecutive EDGES whatever rows they belong to,
+// lane = (edge slot, head); every lane keeps a running (max | sum) for the row its edges are in and merges it with
+// one atomic when its row changes or the quantum ends (combined across the lanes first when the whole warp sits in
+// one row - the hub case).  PASS 0: maxima (seg_max pre-set to -inf), PASS 1: sums of exp(logit - max) (seg_sum
+// pre-set to 0); gat_stats_init_kernel presets both and gives empty segments (0, 1).
+__global__ void __launch_bounds__(kThreads)
+    gat_stats_init_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum, const uint32_t *__restrict__ off,
+                          uint32_t n_rows, uint32_t H) {
+  const uint64_t n = (uint64_t)n_rows * H;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = (uint32_t)(i / H);
+    const bool empty = __ldg(off + r + 1) == __ldg(off + r);
+    seg_max[i] = empty ? 0.f : -INFINITY;
+    seg_sum[i] = empty ? 1.f : 0.f;
+  }
+}
+
+template <int H, int PASS>
+__global__ void __launch_bounds__(kThreads)
+    gat_edge_stats_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum, const float *__restrict__ s_att,
+                          const float *__restrict__ d_att, const uint32_t *__restrict__ row_idx,
+                          const uint32_t *__restrict__ off, const uint32_t *__restrict__ mirror_index,
+                          uint32_t n_rows, float slope) {
+  static_assert(32 % H == 0, "H must divide the warp size");
+  constexpr uint32_t kEdgesPerStep = 32 / H;
+  constexpr int kUnroll = 4;
+  constexpr uint32_t kQuantum = 512;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t h = lane % H, el = lane / H;
+  const uint32_t n_edges = __ldg(off + n_rows);
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t qw = (uint64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); qw * kQuantum < n_edges; qw += nwarps) {
+    const uint32_t e0 = (uint32_t)(qw * kQuantum);
+    const uint32_t e1 = (uint32_t)min((uint64_t)n_edges, (uint64_t)e0 + kQuantum);
+    uint32_t row = eo_find_row(off, n_rows, e0);
+    uint32_t row_end = __ldg(off + row + 1);
+    float dv, mx = 0.f, acc;
+    auto load_row = [&]() {
+      dv = __ldg(d_att + (size_t)row * H + h);
+      if (PASS == 1)
+        mx = seg_max[(size_t)row * H + h]; // written by the previous launch
+      acc = PASS == 0 ? -INFINITY : 0.f;
+    };
+    auto merge = [&](float v) {
+      if (PASS == 0) {
+        if (v > -INFINITY)
+          atomic_max_float(seg_max + (size_t)row * H + h, v);
+      } else if (v != 0.f) {
+        atomicAdd(seg_sum + (size_t)row * H + h, v);
+      }
+    };
+    load_row();
+    for (uint32_t eb = e0 + el; eb < e1; eb += kEdgesPerStep * kUnroll) {
+      float sv[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) {
+        const uint32_t e = eb + u * kEdgesPerStep;
+        sv[u] = e < e1 ? __ldg(s_att + (size_t)slot_at(row_idx, mirror_index, e) * H + h) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; u++) {
+        const uint32_t e = eb + u * kEdgesPerStep;
+        if (e < e1) {
+          if (e >= row_end) {
+            merge(acc);
+            do {
+              row++;
+              row_end = __ldg(off + row + 1);
+            } while (e >= row_end);
+            load_row();
+          }
+          const float x = leaky(sv[u] + dv, slope);
+          acc = PASS == 0 ? fmaxf(acc, x) : acc + expf(x - mx);
+        }
+      }
+    }
+    // end of the quantum: when every lane is still in the same row, combine the lanes of one head first
+    const uint32_t row0 = __shfl_sync(0xffffffffu, row, 0);
+    if (__all_sync(0xffffffffu, row == row0)) {
+#pragma unroll
+      for (int o = 16; o >= H; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = PASS == 0 ? fmaxf(acc, other) : acc + other;
+      }
+      if (el == 0)
+        merge(acc);
+    } else {
+      merge(acc);
+    }
+  }
+}
+
 // Hub segments (> kHubDegree edges; the Zipf generator gives one destination 8.9 M in-edges) are split over
 // kHubSplit CTAs per row: grid = (row blocks, kHubSplit); a CTA looks at the rows of its block and, for hub rows
 // only, reduces its slice of the segment and merges with one atomic per head.  PASS 0: maximum, PASS 1: sum of
 // exp(logit - max) (the maxima must be complete first, hence two launches).
 constexpr uint32_t kHubSplit = 64;
-__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
-  int *a = reinterpret_cast<int *>(addr);
-  int old = *a;
-  while (__int_as_float(old) < v) {
-    const int assumed = old;
-    old = atomicCAS(a, assumed, __float_as_int(v));
-    if (old == assumed)
-      break;
-  }
-}
 
 template <int H, int PASS>
 __global__ void __launch_bounds__(kThreads)
@@ -1094,22 +1186,20 @@ int nts_gat_softmax_stats(float *seg_max, float *seg_sum, const float *src_score
                 "null pointer passed to gat_softmax_stats");
   unsigned grid = (batch_size + kRowsPerCta - 1) / kRowsPerCta;
   cudaStream_t st = as_stream(stream);
-  const dim3 hub_grid(grid, kHubSplit);
 #define NTS_STATS(H_)                                                                                           \
   do {                                                                                                          \
-    gat_softmax_stats_heads_kernel<H_><<<grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,      \
-                                                                    row_indices, column_offset, mirror_index,    \
-                                                                    batch_size, negative_slope, 1);              \
+    gat_stats_init_kernel<<<stream_grid(((uint64_t)batch_size * heads + kThreads - 1) / kThreads), kThreads, 0, \
+                            st>>>(seg_max, seg_sum, column_offset, batch_size, heads);                          \
     count_launch();                                                                                             \
-    gat_hub_stats_kernel<H_, 0><<<hub_grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,         \
-                                                                 row_indices, column_offset, mirror_index,       \
-                                                                 batch_size, negative_slope);                    \
+    gat_edge_stats_kernel<H_, 0><<<full_grid(), kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,      \
+                                                                     row_indices, column_offset, mirror_index,   \
+                                                                     batch_size, negative_slope);                \
     count_launch();                                                                                             \
-    gat_hub_stats_kernel<H_, 1><<<hub_grid, kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,         \
-                                                                 row_indices, column_offset, mirror_index,       \
-                                                                 batch_size, negative_slope);                    \
+    gat_edge_stats_kernel<H_, 1><<<full_grid(), kThreads, 0, st>>>(seg_max, seg_sum, src_score, dst_score,      \
+                                                                     row_indices, column_offset, mirror_index,   \
+                                                                     batch_size, negative_slope);                \
   } while (0)
-  switch (heads) { // all lanes busy when the head count divides the warp
+  switch (heads) { // edge-balanced kernels when the head count divides the warp
   case 1: NTS_STATS(1); break;
   case 2: NTS_STATS(2); break;
   case 4: NTS_STATS(4); break;
@@ -1236,6 +1326,7 @@ int nts_gat_fused_aggregate_backward_two_pass(float *mirror_grad, float *src_sco
     gat_backward_pass_kernel<V_, K_, U_, false, ONE_><<<grid, kThreads, 0, st>>>(                                    \
         nullptr, dst_score_grad, mirror, dst_grad, src_score, pk, row_indices, column_offset, mirror_index,          \
         batch_size, feature_size, heads, negative_slope);                                                            \
+    count_launch();                                                                                                  \
     gat_backward_pass_kernel<V_, K_, U_, true, ONE_><<<grid, kThreads, 0, st>>>(                                     \
         mirror_grad, src_score_grad, dst_grad, mirror, src_score, pk, slot_column_indices, slot_row_offset, nullptr, \
         mirror_size, feature_size, heads, negative_slope);                                                           \
