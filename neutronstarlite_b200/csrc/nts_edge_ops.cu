@@ -366,70 +366,6 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
-// Same statistics with all lanes busy when H divides 32: lane = (edge slot, head), i.e. 32/H edges x H heads per
-// step, and the per-head reductions are xor-shuffles over the lanes that share a head (offsets >= H).
-template <int H>
-__global__ void __launch_bounds__(kThreads)
-    gat_softmax_stats_heads_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum,
-                                   const float *__restrict__ s_att, const float *__restrict__ d_att,
-                                   const uint32_t *__restrict__ row_idx, const uint32_t *__restrict__ off,
-                                   const uint32_t *__restrict__ mirror_index, uint32_t n_rows, float slope,
-                                   int split_hubs) {
-  static_assert(32 % H == 0, "H must divide the warp size");
-  constexpr uint32_t kEdgesPerStep = 32 / H;
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t h = lane % H, el = lane / H;
-  const uint32_t r0 = blockIdx.x * kRowsPerCta;
-  const uint32_t r1 = min(n_rows, r0 + kRowsPerCta);
-  auto head_max = [](float v) {
-#pragma unroll
-    for (int o = 16; o >= H; o >>= 1)
-      v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-  };
-  auto head_sum = [](float v) {
-#pragma unroll
-    for (int o = 16; o >= H; o >>= 1)
-      v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  };
-  for (uint32_t r = r0; r < r1; r++) {
-    const uint32_t b = __ldg(off + r), e = __ldg(off + r + 1);
-    const uint32_t deg = e - b;
-    const bool hub = deg > kHubDegree; // block-uniform
-    if (((r - r0) % kWarps) != wid)
-      continue;
-    if (deg == 0 || (hub && split_hubs)) {
-      // empty segment: (0, 1) so consumers never divide by zero; hub: identity of (max, sum), the segment is
-      // reduced by gat_hub_stats_kernel with many CTAs per row
-      if (lane < H) {
-        seg_max[(size_t)r * H + lane] = deg == 0 ? 0.f : -INFINITY;
-        seg_sum[(size_t)r * H + lane] = deg == 0 ? 1.f : 0.f;
-      }
-      continue;
-    }
-    const uint32_t first = el;
-    const uint32_t step = kEdgesPerStep;
-    const float dv = __ldg(d_att + (size_t)r * H + h);
-    float mx = -INFINITY;
-    for (uint32_t i = first; i < deg; i += step) {
-      const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
-      mx = fmaxf(mx, leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope));
-    }
-    mx = head_max(mx);
-    float sum = 0.f;
-    for (uint32_t i = first; i < deg; i += step) {
-      const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
-      sum += expf(leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope) - mx);
-    }
-    sum = head_sum(sum);
-    if (lane < H) {
-      seg_max[(size_t)r * H + lane] = mx;
-      seg_sum[(size_t)r * H + lane] = sum;
-    }
-  }
-}
-
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
   // IEEE-754 order trick: non-negative floats order like signed ints, negative floats inversely like unsigned ints;
   // one `red` instead of a CAS loop (v + 0.f turns -0.0 into +0.0, NaN never reaches here)
@@ -528,61 +464,6 @@ __global__ void __launch_bounds__(kThreads)
         merge(acc);
     } else {
       merge(acc);
-    }
-  }
-}
-
-// Hub segments (> kHubDegree edges; the Zipf generator gives one destination 8.9 M in-edges) are split over
-// kHubSplit CTAs per row: grid = (row blocks, kHubSplit); a CTA looks at the rows of its block and, for hub rows
-// only, reduces its slice of the segment and merges with one atomic per head.  PASS 0: maximum, PASS 1: sum of
-// exp(logit - max) (the maxima must be complete first, hence two launches).
-constexpr uint32_t kHubSplit = 64;
-
-template <int H, int PASS>
-__global__ void __launch_bounds__(kThreads)
-    gat_hub_stats_kernel(float *__restrict__ seg_max, float *__restrict__ seg_sum, const float *__restrict__ s_att,
-                         const float *__restrict__ d_att, const uint32_t *__restrict__ row_idx,
-                         const uint32_t *__restrict__ off, const uint32_t *__restrict__ mirror_index, uint32_t n_rows,
-                         float slope) {
-  static_assert(32 % H == 0, "H must divide the warp size");
-  constexpr uint32_t kEdgesPerStep = 32 / H;
-  __shared__ float scratch[kWarps][32];
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const uint32_t h = lane % H, el = lane / H;
-  const uint32_t r0 = blockIdx.x * kRowsPerCta;
-  const uint32_t r1 = min(n_rows, r0 + kRowsPerCta);
-  for (uint32_t r = r0; r < r1; r++) {
-    const uint32_t b = __ldg(off + r), e = __ldg(off + r + 1);
-    const uint32_t deg = e - b;
-    if (deg <= kHubDegree)
-      continue; // block-uniform
-    const uint32_t per = (deg + kHubSplit - 1) / kHubSplit;
-    const uint32_t lo = min(deg, blockIdx.y * per), hi = min(deg, lo + per);
-    const float dv = __ldg(d_att + (size_t)r * H + h);
-    const float mx_all = PASS == 1 ? __ldg(seg_max + (size_t)r * H + h) : 0.f;
-    float acc = PASS == 0 ? -INFINITY : 0.f;
-    for (uint32_t i = lo + wid * kEdgesPerStep + el; i < hi; i += kWarps * kEdgesPerStep) {
-      const uint32_t slot = slot_at(row_idx, mirror_index, b + i);
-      const float x = leaky(__ldg(s_att + (size_t)slot * H + h) + dv, slope);
-      acc = PASS == 0 ? fmaxf(acc, x) : acc + expf(x - mx_all);
-    }
-#pragma unroll
-    for (int o = 16; o >= H; o >>= 1) {
-      const float other = __shfl_xor_sync(0xffffffffu, acc, o);
-      acc = PASS == 0 ? fmaxf(acc, other) : acc + other;
-    }
-    __syncthreads();
-    scratch[wid][lane] = acc;
-    __syncthreads();
-    if (wid == 0 && lane < H) {
-      float v = scratch[0][lane];
-#pragma unroll
-      for (int w2 = 1; w2 < kWarps; w2++)
-        v = PASS == 0 ? fmaxf(v, scratch[w2][lane]) : v + scratch[w2][lane];
-      if (PASS == 0)
-        atomic_max_float(seg_max + (size_t)r * H + lane, v);
-      else if (v != 0.f)
-        atomicAdd(seg_sum + (size_t)r * H + lane, v);
     }
   }
 }
