@@ -291,6 +291,51 @@ int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t f
 /* dX_p += sum_j A_{j<-p}^T dY_j (ForwardGPUfuseOp::backward, :75-90); dx zeroed by caller */
 int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t feature_size, void *stream);
 
+/* ---- exchange plan builder (host C++): the reference's chunks -> the arrays of nts_exchange_desc ------------------------
+ * C++ twin of neutronstarlite_b200/exchange.py::ExchangePlan for hosts without Python (the reference's own host
+ * code: include/nts_dropin/core/ntsDistGPUFusedGraphOp.hpp).  One nts_host_chunk per source partition i describes
+ * CSC_segment_pinned `graph_chunks[i]` of this rank (core/GraphSegment.h:52-139) through its HOST arrays:
+ * column_offset[V_p+1] / row_indices[E_i] (global source ids) / edge_weight_forward, row_offset[V_i+1] /
+ * column_indices[E_i] (global destination ids) / edge_weight_backward, src_range, dst_range, edge_size.
+ * Sequence:  create -> pack_needs -> (caller moves every rank's pack to every rank) -> set_peer_needs for each
+ * peer -> finalize -> create_from_plan (uploads; the plan owns the device copies and must outlive the engine). */
+typedef struct nts_host_chunk {
+  const nts_vid_t *column_offset, *row_indices, *row_offset, *column_indices;
+  const float *edge_weight_forward, *edge_weight_backward;
+  nts_vid_t src_start, src_end, dst_start, dst_end;
+  uint64_t edges;
+} nts_host_chunk;
+typedef struct nts_exchange_plan nts_exchange_plan;
+nts_exchange_plan *nts_exchange_plan_create(const nts_host_chunk *chunks, int partitions, int rank);
+void nts_exchange_plan_destroy(nts_exchange_plan *plan);
+/* rows of partition i (local ids, ascending) that have an edge into this rank's partition = what it reads from i */
+const nts_vid_t *nts_exchange_plan_need(const nts_exchange_plan *plan, int i, nts_vid_t *count);
+/* this rank's lists in wire form: need_counts[P] (own entry 0) and the lists concatenated in partition order */
+uint64_t nts_exchange_plan_packed_rows(const nts_exchange_plan *plan);
+int nts_exchange_plan_pack_needs(const nts_exchange_plan *plan, nts_vid_t *need_counts, nts_vid_t *need_rows);
+/* rank j's wire form, as received */
+int nts_exchange_plan_set_peer_needs(nts_exchange_plan *plan, int j, const nts_vid_t *need_counts,
+                                     const nts_vid_t *need_rows);
+int nts_exchange_plan_finalize(nts_exchange_plan *plan);
+/* host view of the finalized plan (tests, other transports); pointers live as long as the plan */
+typedef struct nts_exchange_plan_view {
+  int partitions, rank;
+  nts_vid_t owned_vertices, recv_total, send_total, backward_rows;
+  uint64_t remote_edges;
+  const nts_vid_t *need_count, *send_count, *peer_bwd_offset;   /* [P] each */
+  const nts_vid_t *remote_column_offset, *remote_slots;         /* [V_p+1], [remote_edges] */
+  const float *remote_weight;
+  const nts_vid_t *backward_offsets, *backward_indices;         /* [backward_rows+1], [remote_edges] */
+  const float *backward_weight;
+  const nts_vid_t *send_rows_all;                               /* [send_total] */
+} nts_exchange_plan_view;
+int nts_exchange_plan_get_view(const nts_exchange_plan *plan, nts_exchange_plan_view *view);
+/* the six pointers are the DEVICE arrays of the local chunk graph_chunks[rank] (CopyGraphToDevice) */
+nts_exchange *nts_exchange_create_from_plan(nts_exchange_plan *plan, const nts_vid_t *local_column_offset,
+                                            const nts_vid_t *local_row_indices, const float *local_weight_forward,
+                                            const nts_vid_t *local_row_offset, const nts_vid_t *local_column_indices,
+                                            const float *local_weight_backward);
+
 /* ---- host-side graph preparation (C++ with OpenMP; no device involved) -----------------------------------
  * Restates the layout contract of core/graph.hpp:1185-1211 (partitioner), :4396-4401 (degree clamp),
  * core/ntsBaseOp.hpp:194-197 (edge weight) and core/PartitionedGraph.hpp:324-420 (per-source-partition chunks). */

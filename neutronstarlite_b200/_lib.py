@@ -111,6 +111,44 @@ SIGNATURES.update({
     "nts_exchange_backward": (_int, [_vp, _vp, _vp, _u32, _vp]),
 })
 
+
+
+class HostChunk(C.Structure):
+    """nts_host_chunk of include/nts_b200.h (host arrays of one CSC_segment_pinned)."""
+    _fields_ = [
+        ("column_offset", _vp), ("row_indices", _vp), ("row_offset", _vp), ("column_indices", _vp),
+        ("edge_weight_forward", _vp), ("edge_weight_backward", _vp),
+        ("src_start", _u32), ("src_end", _u32), ("dst_start", _u32), ("dst_end", _u32), ("edges", _u64),
+    ]
+
+
+class ExchangePlanView(C.Structure):
+    """nts_exchange_plan_view of include/nts_b200.h."""
+    _fields_ = [
+        ("partitions", _int), ("rank", _int),
+        ("owned_vertices", _u32), ("recv_total", _u32), ("send_total", _u32), ("backward_rows", _u32),
+        ("remote_edges", _u64),
+        ("need_count", C.POINTER(_u32)), ("send_count", C.POINTER(_u32)), ("peer_bwd_offset", C.POINTER(_u32)),
+        ("remote_column_offset", C.POINTER(_u32)), ("remote_slots", C.POINTER(_u32)),
+        ("remote_weight", C.POINTER(C.c_float)),
+        ("backward_offsets", C.POINTER(_u32)), ("backward_indices", C.POINTER(_u32)),
+        ("backward_weight", C.POINTER(C.c_float)),
+        ("send_rows_all", C.POINTER(_u32)),
+    ]
+
+
+SIGNATURES.update({
+    "nts_exchange_plan_create": (_vp, [C.POINTER(HostChunk), _int, _int]),
+    "nts_exchange_plan_destroy": (None, [_vp]),
+    "nts_exchange_plan_need": (C.POINTER(_u32), [_vp, _int, C.POINTER(_u32)]),
+    "nts_exchange_plan_packed_rows": (_u64, [_vp]),
+    "nts_exchange_plan_pack_needs": (_int, [_vp, _vp, _vp]),
+    "nts_exchange_plan_set_peer_needs": (_int, [_vp, _int, _vp, _vp]),
+    "nts_exchange_plan_finalize": (_int, [_vp]),
+    "nts_exchange_plan_get_view": (_int, [_vp, C.POINTER(ExchangePlanView)]),
+    "nts_exchange_create_from_plan": (_vp, [_vp] * 7),
+})
+
 _lib = None
 
 

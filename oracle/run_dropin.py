@@ -180,6 +180,9 @@ def main():
     ap.add_argument("--algos", default="GCNEAGERSINGLE,GCN,GATGPUDIST,test_getdep")
     ap.add_argument("-np", type=int, default=1, help="ranks of the reference's host code (MPI stand-in); P > 1 runs "
                     "its sync_compute_decoupled / compute_sync_decoupled exchange on top of our kernels")
+    ap.add_argument("--dist-exchange", action="store_true",
+                    help="use nts_dropin_dist_main (make -C oracle dropin_dist): ForwardGPUfuseOp on the device-resident "
+                         "peer-memory exchange instead of the reference's host-staged MPI exchange")
     ap.add_argument("--synthetic", type=int, default=0, metavar="DIV",
                     help="compare ours vs the reference's own kernels through the reference's host code on 1/DIV of "
                          "the Reddit-shaped graph")
@@ -188,11 +191,12 @@ def main():
         return synthetic_main(a.synthetic, min(a.epochs, 6))
     res = {}
     cpu = os.path.join(REF, "nts_ref_main")
-    gpu = os.path.join(REF, "nts_dropin_main")
+    gpu = os.path.join(REF, "nts_dropin_dist_main" if a.dist_exchange else "nts_dropin_main")
+    res["binary"] = os.path.basename(gpu)
     res["cpu_reference_GCNCPU"] = run(cpu, "GCNCPU", a.epochs, nprocs=a.np)
     for algo in a.algos.split(","):
         try:
-            res["dropin_" + algo] = run(gpu, algo, a.epochs, nprocs=a.np)
+            res["dropin_" + algo] = run(gpu, algo, a.epochs, nprocs=a.np, timeout=240)
         except subprocess.TimeoutExpired:
             res["dropin_" + algo] = {"algo": algo, "rc": "timeout"}
     print(json.dumps(res, indent=1))
