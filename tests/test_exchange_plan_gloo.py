@@ -38,6 +38,62 @@ def _a2a(parts_out, counts_in, F):
     return out
 
 
+def _check_cxx_plan(pg, plan, rank, P):
+    """The C++ plan builder (nts_exchange_plan_*, what the reference's C++ host uses) must produce exactly the arrays
+    of the Python ExchangePlan: the wire form of the need lists travels over gloo here, over MPI_Bcast there."""
+    import ctypes as C
+    from neutronstarlite_b200 import _lib
+    L = _lib.load()
+    arr = (_lib.HostChunk * P)()
+    for i, c in enumerate(pg.graph_chunks):
+        h = arr[i]
+        for name in ("column_offset", "row_indices", "row_offset", "column_indices", "edge_weight_forward",
+                     "edge_weight_backward"):
+            setattr(h, name, getattr(c, name).ctypes.data_as(C.c_void_p))
+        h.src_start, h.src_end = int(c.src_range[0]), int(c.src_range[1])
+        h.dst_start, h.dst_end = int(c.dst_range[0]), int(c.dst_range[1])
+        h.edges = int(c.edge_size)
+    cp = L.nts_exchange_plan_create(arr, P, rank)
+    assert cp, L.nts_last_error()
+    try:
+        n = int(L.nts_exchange_plan_packed_rows(cp))
+        counts = np.zeros(P, dtype=np.uint32)
+        rows = np.zeros(max(n, 1), dtype=np.uint32)
+        assert L.nts_exchange_plan_pack_needs(cp, counts.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.c_void_p)) == 0
+        packs = [None] * P
+        dist.all_gather_object(packs, (counts, rows[:n]))
+        for j, (cj, rj) in enumerate(packs):
+            rj = np.ascontiguousarray(np.concatenate([rj, np.zeros(1, dtype=np.uint32)]))
+            assert L.nts_exchange_plan_set_peer_needs(cp, j, cj.ctypes.data_as(C.c_void_p),
+                                                      rj.ctypes.data_as(C.c_void_p)) == 0, L.nts_last_error()
+        assert L.nts_exchange_plan_finalize(cp) == 0, L.nts_last_error()
+        v = _lib.ExchangePlanView()
+        assert L.nts_exchange_plan_get_view(cp, C.byref(v)) == 0
+
+        def arr_of(ptr, m, dt):
+            return np.ctypeslib.as_array(ptr, shape=(m,)).astype(dt, copy=True) if m and ptr else np.zeros(0, dtype=dt)
+
+        assert (v.recv_total, v.send_total, int(v.remote_edges)) == (plan.recv_total, plan.send_total, plan.remote_edges)
+        assert list(arr_of(v.need_count, P, np.uint32)) == [plan.need_count[i] if i != rank else 0 for i in range(P)]
+        assert list(arr_of(v.send_count, P, np.uint32)) == [plan.send_count[j] if j != rank else 0 for j in range(P)]
+        u32 = lambda t: t.numpy().view(np.uint32) if t.dtype == torch.int32 else t.numpy()
+        E = plan.remote_edges
+        if E:
+            assert np.array_equal(arr_of(v.remote_column_offset, pg.owned_vertices + 1, np.uint32), u32(plan.remote_col_offset))
+            assert np.array_equal(arr_of(v.remote_slots, E, np.uint32), u32(plan.remote_slots))
+            assert np.array_equal(arr_of(v.remote_weight, E, np.float32).view(np.uint32), plan.remote_w.numpy().view(np.uint32))
+            assert np.array_equal(arr_of(v.backward_indices, E, np.uint32), u32(plan.bwd_indices))
+            assert np.array_equal(arr_of(v.backward_weight, E, np.float32).view(np.uint32), plan.bwd_w.numpy().view(np.uint32))
+        assert np.array_equal(arr_of(v.backward_offsets, v.backward_rows + 1, np.uint32), u32(plan.bwd_offsets))
+        assert np.array_equal(arr_of(v.send_rows_all, v.send_total, np.uint32), u32(plan.send_rows_all))
+        # peer_bwd_offset as exchange.py::_PeerWindows derives it
+        allc = [None] * P
+        dist.all_gather_object(allc, [plan.need_count[i] if i != rank else 0 for i in range(P)])
+        assert list(arr_of(v.peer_bwd_offset, P, np.uint32)) == [int(sum(allc[j][:rank])) for j in range(P)]
+    finally:
+        L.nts_exchange_plan_destroy(cp)
+
+
 def _worker(rank, world, port, case, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -115,6 +171,7 @@ def _worker(rank, world, port, case, q):
             if i != rank:
                 mirror_bits = z["r%d/chunk%d_has_mirror_at" % (rank, i)]  # my rows partition i needs
                 assert np.array_equal(np.nonzero(mirror_bits)[0], plan.send_rows[i].numpy())
+        _check_cxx_plan(pg, plan, rank, P)
         q.put((rank, "ok"))
     except Exception as exc:  # pragma: no cover - surfaced in the parent
         import traceback
