@@ -248,3 +248,33 @@ def test_input_buffer_can_be_swapped_between_epochs(fake_ops, eager):
         lb, _ = b.run_epoch()
         torch.testing.assert_close(la, lb)
     assert time.perf_counter() - t0 < 20
+
+
+def test_slot_indices_and_slot_csr_on_reference_partitions(golden):
+    """Setup-time index structures of the fused GAT layer (torch ops, device-agnostic) on the reference's own
+    whole-partition CSC + MirrorIndex at P = 1, 2, 4, 8: the slot CSR must list exactly the CSC's edges, keyed by
+    mirror slot, and every mirror slot must own at least one edge."""
+    import types
+    g = golden
+    for r in range(g.P):
+        pg = types.SimpleNamespace()
+        pg.column_offset_gpu = torch.from_numpy(g.get(r, "whole_column_offset").astype(np.int32))
+        pg.row_indices_gpu = torch.from_numpy(g.get(r, "whole_row_indices").astype(np.int32))
+        pg.mirror_index_gpu = torch.from_numpy(g.get(r, "mirror_index").astype(np.int32))
+        meta = g.get(r, "meta")
+        pg.owned_vertices, pg.owned_edges, pg.owned_mirrors = int(meta[4]), int(meta[5]), int(meta[6])
+        slots = ops.DistGPUFusedGATOp.slot_indices(pg)
+        assert slots.dtype == torch.int32 and slots.numel() == pg.owned_edges
+        if pg.owned_edges == 0:
+            continue
+        assert int(slots.max()) < pg.owned_mirrors and int(slots.min()) >= 0
+        off, dst = ops.DistGPUFusedGATOp.slot_csr(pg)
+        off, dst = off.long(), dst.long()
+        assert off.numel() == pg.owned_mirrors + 1 and int(off[0]) == 0 and int(off[-1]) == pg.owned_edges
+        assert bool((off[1:] > off[:-1]).all()), "a mirror slot without edges"
+        col = pg.column_offset_gpu.long()
+        csc_dst = torch.repeat_interleave(torch.arange(pg.owned_vertices), col[1:] - col[:-1])
+        csc_pairs = torch.sort(slots.long() * pg.owned_vertices + csc_dst).values
+        csr_slot = torch.repeat_interleave(torch.arange(pg.owned_mirrors), off[1:] - off[:-1])
+        csr_pairs = torch.sort(csr_slot * pg.owned_vertices + dst).values
+        assert torch.equal(csc_pairs, csr_pairs)
