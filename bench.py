@@ -221,6 +221,8 @@ def _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores):
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: keep NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) off it
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import numpy as np
     import torch
     import torch.distributed as dist
