@@ -39,6 +39,12 @@ def _np(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
 
 
+def _need(plan, i):
+    cnt = C.c_uint32(0)
+    ptr = _lib.load().nts_exchange_plan_need(plan, i, C.byref(cnt))
+    return _np(ptr, cnt.value, np.uint32)
+
+
 class _Rank:
     def __init__(self, g, r):
         L = _lib.load()
@@ -108,14 +114,7 @@ def test_plan_replays_the_reference_exchange(golden):
         po = g.partition_offset.astype(np.int64)
         X = [g.mat(r, "X").astype(np.float32) for r in range(g.P)]
         G = [g.mat(r, "G").astype(np.float32) for r in range(g.P)]
-        need = []
-        for r, a in enumerate(ranks):
-            lists = []
-            for i in range(g.P):
-                cnt = C.c_uint32(0)
-                ptr = L.nts_exchange_plan_need(a.plan, i, C.byref(cnt))
-                lists.append(_np(ptr, cnt.value, np.uint32))
-            need.append(lists)
+        need = [[_need(a.plan, i) for i in range(g.P)] for a in ranks]
         # consistency of the two directions: what j sends to r is what r needs from j
         for r in range(g.P):
             v = views[r]
@@ -203,3 +202,113 @@ def test_plan_rejects_incomplete_and_bad_input():
         assert v.recv_total == 0 and v.send_total == 0 and v.remote_edges == 0 and v.backward_rows == 0
     finally:
         L.nts_exchange_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("V,E,P,seed", [(5000, 40000, 3, 1), (3000, 9000, 4, 2), (9000, 200, 5, 3), (2048, 30000, 2, 4),
+                                        (7000, 60000, 6, 5)])
+def test_plan_on_random_graphs_matches_dense_product(V, E, P, seed):
+    """Chunks from the product's own host builder (random multigraphs, hubs, partitions left empty by the 1024-aligned
+    partitioner, ranks without remote edges), plan from the C++ builder, exchange replayed in numpy: Y = A X and
+    dX = A^T G against a float64 scatter over the edge list."""
+    from neutronstarlite_b200.graph import HostGraph, PartitionedGraph
+    L = _lib.load()
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, V, E, dtype=np.uint32)
+    dst = rng.integers(0, V, E, dtype=np.uint32)
+    hub = rng.integers(0, V)
+    dst[: E // 5] = hub                                  # one hub destination
+    src[E // 5: E // 3] = rng.integers(0, V)             # and one hub source
+    edges = np.stack([src, dst], 1)
+    hg = HostGraph(edges, V)
+    F = 3
+    X = rng.uniform(-1, 1, (V, F)).astype(np.float32)
+    G = rng.uniform(-1, 1, (V, F)).astype(np.float32)
+    pgs = [PartitionedGraph(hg, P, r).generate_all(dist=True) for r in range(P)]
+    po = pgs[0].partition_offset.astype(np.int64)
+    out_d, in_d = hg.degrees()
+    w = (1.0 / (np.sqrt(out_d[src].astype(np.float64)).astype(np.float32) *
+                np.sqrt(in_d[dst].astype(np.float64)).astype(np.float32))).astype(np.float32)
+    Y_ref = np.zeros((V, F))
+    np.add.at(Y_ref, dst.astype(np.int64), X[src.astype(np.int64)].astype(np.float64) * w[:, None])
+    dX_ref = np.zeros((V, F))
+    np.add.at(dX_ref, src.astype(np.int64), G[dst.astype(np.int64)].astype(np.float64) * w[:, None])
+
+    plans, packs, keep = [], [], []
+    try:
+        for r in range(P):
+            arr = (_lib.HostChunk * P)()
+            for i, c in enumerate(pgs[r].graph_chunks):
+                h = arr[i]
+                for name in ("column_offset", "row_indices", "row_offset", "column_indices", "edge_weight_forward",
+                             "edge_weight_backward"):
+                    setattr(h, name, getattr(c, name).ctypes.data_as(C.c_void_p))
+                h.src_start, h.src_end = int(c.src_range[0]), int(c.src_range[1])
+                h.dst_start, h.dst_end = int(c.dst_range[0]), int(c.dst_range[1])
+                h.edges = int(c.edge_size)
+            keep.append(arr)
+            pl = L.nts_exchange_plan_create(arr, P, r)
+            assert pl, L.nts_last_error()
+            plans.append(pl)
+            n = int(L.nts_exchange_plan_packed_rows(pl))
+            counts = np.zeros(P, dtype=np.uint32)
+            rows = np.zeros(n + 1, dtype=np.uint32)
+            assert L.nts_exchange_plan_pack_needs(pl, _u32p(counts), _u32p(rows)) == 0
+            packs.append((counts, rows))
+        views = []
+        for r in range(P):
+            for j in range(P):
+                assert L.nts_exchange_plan_set_peer_needs(plans[r], j, _u32p(packs[j][0]), _u32p(packs[j][1])) == 0, \
+                    L.nts_last_error()
+            assert L.nts_exchange_plan_finalize(plans[r]) == 0, L.nts_last_error()
+            v = _lib.ExchangePlanView()
+            assert L.nts_exchange_plan_get_view(plans[r], C.byref(v)) == 0
+            views.append(v)
+        need = [[_need(plans[r], i) for i in range(P)] for r in range(P)]
+        partial = []
+        for r in range(P):
+            v = views[r]
+            Vp = int(po[r + 1] - po[r])
+            c = pgs[r].graph_chunks[r]
+            y = np.zeros((Vp, F))
+            if c.edge_size:
+                y += _segment_sum(c.column_offset, c.row_indices.astype(np.int64) - po[r], c.edge_weight_forward,
+                                  X[po[r]:po[r + 1]], Vp)
+            stag = [X[po[i]:po[i + 1]][need[r][i]] for i in range(P) if i != r]
+            stag = np.concatenate(stag) if stag else np.zeros((0, F), dtype=np.float32)
+            assert stag.shape[0] == v.recv_total
+            E_r = int(v.remote_edges)
+            if E_r:
+                y += _segment_sum(_np(v.remote_column_offset, Vp + 1, np.uint32), _np(v.remote_slots, E_r, np.uint32),
+                                  _np(v.remote_weight, E_r, np.float32), stag, Vp)
+            _close(y, Y_ref[po[r]:po[r + 1]])
+            rows = v.backward_rows
+            assert rows == v.recv_total
+            if E_r:
+                part = _segment_sum(_np(v.backward_offsets, rows + 1, np.uint32),
+                                    _np(v.backward_indices, E_r, np.uint32).astype(np.int64) - po[r],
+                                    _np(v.backward_weight, E_r, np.float32), G[po[r]:po[r + 1]], rows)
+            else:
+                part = np.zeros((rows, F))
+            partial.append(part)
+        for r in range(P):
+            v = views[r]
+            Vp = int(po[r + 1] - po[r])
+            c = pgs[r].graph_chunks[r]
+            dx = np.zeros((Vp, F))
+            if c.edge_size:
+                dx += _segment_sum(c.row_offset, c.column_indices.astype(np.int64) - po[r], c.edge_weight_backward,
+                                   G[po[r]:po[r + 1]], Vp)
+            send_rows = _np(v.send_rows_all, v.send_total, np.uint32).astype(np.int64)
+            send_count = _np(v.send_count, P, np.uint32)
+            off = _np(v.peer_bwd_offset, P, np.uint32)
+            pos = 0
+            for j in range(P):
+                if j == r:
+                    continue
+                n = int(send_count[j])
+                np.add.at(dx, send_rows[pos:pos + n], partial[j][int(off[j]):int(off[j]) + n])
+                pos += n
+            _close(dx, dX_ref[po[r]:po[r + 1]])
+    finally:
+        for pl in plans:
+            L.nts_exchange_plan_destroy(pl)
