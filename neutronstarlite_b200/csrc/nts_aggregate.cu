@@ -630,6 +630,8 @@ int nts_gather_by_dst_from_src(const float *input, float *output, const float *w
   (void)src_end;
   (void)dst_start;
   (void)dst_end;
+  if (batch_size == 0 || edges == 0 || feature_size == 0) // empty chunk / empty partition: nothing to add
+    return 0;
   NTS_ARG_CHECK(!with_weight || weight_forward, "with_weight set but weight pointer is null");
   return nts::segment_gather_sum(input, output, with_weight ? weight_forward : nullptr, row_indices, column_offset,
                                  nullptr, src_start, batch_size, edges, feature_size, nts::as_stream(stream));
@@ -642,6 +644,8 @@ int nts_gather_by_src_from_dst(const float *input, float *output, const float *w
   (void)src_start;
   (void)src_end;
   (void)dst_end;
+  if (batch_size == 0 || edges == 0 || feature_size == 0)
+    return 0;
   NTS_ARG_CHECK(!with_weight || weight_backward, "with_weight set but weight pointer is null");
   return nts::segment_gather_sum(input, output, with_weight ? weight_backward : nullptr, column_indices, row_offset,
                                  nullptr, dst_start, batch_size, edges, feature_size, nts::as_stream(stream));

@@ -226,8 +226,11 @@ static int signal_consumed(nts_exchange *ex, uint32_t epoch, cudaStream_t st) {
 
 // Y_p += sum_i A_{p<-i} X_i.  `y` must be zeroed by the caller (accumulate semantics, like every aggregation entry).
 int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t F, void *stream) {
-  NTS_ARG_CHECK(ex && x && y, "null argument");
+  NTS_ARG_CHECK(ex != nullptr, "null engine");
   const nts_exchange_desc &d = ex->d;
+  // a rank that owns no vertices (the 1024-aligned partitioner leaves such ranks on small graphs) has no rows to
+  // publish or produce, but still takes part in the flag protocol below
+  NTS_ARG_CHECK(d.owned_vertices == 0 || (x && y), "null feature pointer");
   cudaStream_t st = as_stream(stream);
   const int P = d.partitions, p = d.rank;
   if (P == 1)
@@ -266,8 +269,9 @@ int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t F
 
 // dX_p += sum_j A_{j<-p}^T dY_j.  `dx` must be zeroed by the caller.
 int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t F, void *stream) {
-  NTS_ARG_CHECK(ex && g && dx, "null argument");
+  NTS_ARG_CHECK(ex != nullptr, "null engine");
   const nts_exchange_desc &d = ex->d;
+  NTS_ARG_CHECK(d.owned_vertices == 0 || (g && dx), "null gradient pointer");
   cudaStream_t st = as_stream(stream);
   const int P = d.partitions, p = d.rank;
   if (P == 1)

@@ -46,6 +46,17 @@ def test_argument_errors_are_reported_not_swallowed():
     assert lib.nts_aggregate_set_variant(0, 0) == 0
 
 
+def test_empty_chunks_are_a_no_op_before_any_pointer_is_looked_at():
+    """A rank that owns no vertices (or a chunk without edges) hands the aggregation entries empty tensors, whose data
+    pointers are NULL: the entries must return success without touching CUDA or complaining about the pointers."""
+    lib = _lib.load()
+    for name in ("nts_gather_by_dst_from_src", "nts_gather_by_src_from_dst"):
+        fn = getattr(lib, name)
+        assert fn(None, None, None, None, None, 0, 0, 0, 0, 0, 0, 16, 1, None) == 0      # no rows
+        assert fn(None, None, None, None, None, 0, 8, 0, 8, 0, 8, 16, 1, None) == 0      # rows but no edges
+    assert lib.nts_segment_gather_sum(None, None, None, None, None, 0, 0, 0, 16, None) == 0
+
+
 def test_bench_reference_arm_prints_the_contract_keys():
     """`bench.py --impl reference` (CPU only: the unmodified reference GCNCPU, or the C port when oracle/_ref is
     absent) on the tiny workload: one JSON line with the keys the driver reads."""
