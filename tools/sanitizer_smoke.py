@@ -48,5 +48,8 @@ for H, D in ((1, 16), (4, 8)):
     fused = ops.DistGPUFusedGATOp(pg)
     out = fused.forward(mirror, mirror[:, :H].contiguous(), x[:, :H].contiguous())
     fused.backward(out)
+    single = ops.DistGPUFusedGATOp(pg, two_pass_backward=False)   # the single-pass (atomic) backward as well
+    single.forward(mirror, mirror[:, :H].contiguous(), x[:, :H].contiguous())
+    single.backward(out)
 torch.cuda.synchronize()
 print("sanitizer smoke done, launches:", _lib.load().nts_kernel_launch_count())
