@@ -3,7 +3,9 @@
   * `Parameter`  <-> core/NtsScheduler.hpp:639-791 (weight, L2-regularised Adam with the reference's bias-correction
                      folded into alpha by `next()`, gradient SUM-allreduce - NCCL instead of MPI on host copies)
   * `GCNImpl`    <-> toolkits/GCN.hpp (2-layer GCN: aggregate -> X.W -> relu / log_softmax, nll loss on the train
-                     mask, tape backward, Adam) and toolkits/GCN_EAGER_single.hpp for the single-GPU op.
+                     mask, tape backward, Adam); the single-GPU op of toolkits/GCN_EAGER_single.hpp when P = 1.
+  * `GCNEagerImpl` <-> toolkits/GCN_EAGER_single.hpp / GCN_EAGER.hpp order (X.W first, aggregate the narrow result).
+  * `GATImpl`    <-> the flow of toolkits/GAT_CPU_DIST_OPTM.hpp on the fused multi-head aggregation (K7).
 
 Dense NN work (mm, relu, log_softmax, nll_loss, Adam element-wise) stays on torch/cuBLAS exactly as in the
 reference (libtorch); the aggregation goes through libnts_b200."""
