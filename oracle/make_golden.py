@@ -3,7 +3,7 @@
 
 Runs oracle/_ref/nts_ref_driver (built by `make -C oracle ref` from /root/reference) on
   * the reference's own Cora fixture (data/cora.2708.edge.self) at P = 1, 2, 4 ranks and
-  * a small synthetic multigraph (hubs, duplicates, self loops, isolated vertices) at P = 1, 2, 4, 8
+  * a small synthetic multigraph (hubs, duplicates, self loops, isolated vertices) at P = 1, 2, 3, 4, 8
 and packs every dumped artefact into one .npz per case.  Only runs in the build container
 (/root/reference must exist); the .npz files are committed so the GPU box never needs it.
 
@@ -120,6 +120,12 @@ def run_case(name, edges, V, P, F, keep_copy_only, threads):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--synth-only":   # python oracle/make_golden.py --synth-only 3 5
+        os.makedirs(GOLD, exist_ok=True)
+        syn = synth_edges()
+        for P in (int(x) for x in sys.argv[2:]):
+            run_case("synth9k", syn, 9216, P, 2, False, max(1, 4 // P))
+        return
     if not os.path.exists(DRIVER):
         subprocess.check_call(["make", "-C", HERE, "ref"])
     os.makedirs(GOLD, exist_ok=True)
@@ -128,7 +134,7 @@ def main():
     run_case("cora_self", cora, 2708, 2, 4, True, 2)
     run_case("cora_self", cora, 2708, 4, 2, False, 1)   # two EMPTY partitions (1024-vertex page rounding)
     syn = synth_edges()
-    for P in (1, 2, 4, 8):
+    for P in (1, 2, 3, 4, 8):                            # 3: a ring that is not a power of two
         run_case("synth9k", syn, 9216, P, 2, False, max(1, 4 // P))
 
 

@@ -181,7 +181,8 @@ def _worker(rank, world, port, case, q):
 
 
 @pytest.mark.parametrize("case,world,port", [("synth9k_P2_F2.npz", 2, 29611), ("cora_self_P2_F4.npz", 2, 29612),
-                                             ("synth9k_P4_F2.npz", 4, 29613), ("cora_self_P4_F2.npz", 4, 29614)])
+                                             ("synth9k_P4_F2.npz", 4, 29613), ("cora_self_P4_F2.npz", 4, 29614),
+                                             ("synth9k_P3_F2.npz", 3, 29615)])
 def test_exchange_plan_matches_reference(case, world, port):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
