@@ -103,3 +103,40 @@ def test_duplicates_and_self_loops_count_in_degrees():
     w = 1 / (np.sqrt(out_d[c.row_indices].astype(np.float64)).astype(np.float32) *
              np.sqrt(in_d[[0, 1, 1, 1, 1]].astype(np.float64)).astype(np.float32))
     assert np.array_equal(c.edge_weight_forward, w.astype(np.float32))
+
+
+def test_host_builder_equals_the_pinned_oracle_on_random_graphs():
+    """Beyond the golden cases: random multigraphs x partition counts (incl. non-powers of two and partitions the
+    1024-aligned partitioner leaves empty).  The numpy restatement is pinned against the reference's own dumps
+    (tests/test_oracle_golden.py); the product's C++ host builder must agree with it bit for bit here."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import nts_oracle as O   # checker only
+    rng = np.random.default_rng(7)
+    for V, E, P in [(3000, 20000, 3), (7000, 50000, 5), (12000, 9000, 7), (2048, 4000, 2), (1500, 6000, 4),
+                    (20000, 120000, 6)]:
+        src = rng.integers(0, V, E).astype(np.uint32)
+        dst = (rng.zipf(1.3, E) % V).astype(np.uint32)          # skewed destinations
+        src[: E // 10] = rng.integers(0, V)                     # one hub source
+        edges = np.stack([src, dst], 1)
+        hg = HostGraph(edges, V)
+        out_d, in_d = hg.degrees()
+        o_out, o_in = O.degrees(edges, V)
+        assert np.array_equal(out_d, o_out) and np.array_equal(in_d, o_in)
+        po = hg.partition_offsets(P)
+        assert np.array_equal(po, O.partition_offsets(edges, V, P))
+        for r in range(P):
+            pg = PartitionedGraph(hg, P, r).generate_all(dist=True)
+            ref = O.build_chunks(edges, V, po, r, o_out, o_in)
+            for c, rc in zip(pg.graph_chunks, ref):
+                assert c.edge_size == rc.edge_size and tuple(c.src_range) == tuple(rc.src_range)
+                assert np.array_equal(c.column_offset, rc.column_offset)
+                assert np.array_equal(c.row_indices, rc.row_indices)
+                assert np.array_equal(c.edge_weight_forward.view(np.uint32), rc.edge_weight_forward.view(np.uint32))
+                assert np.array_equal(c.row_offset, rc.row_offset)
+                assert np.array_equal(rows_as_multisets(c.row_offset, c.column_indices),
+                                      rows_as_multisets(rc.row_offset, rc.column_indices))
+                assert np.array_equal(c.source_active, rc.source_active)
+            mi, n_mirrors = O.mirror_index(edges, V, po, r)
+            assert np.array_equal(pg.MirrorIndex, mi) and pg.owned_mirrors == n_mirrors
