@@ -42,11 +42,16 @@ def parse_args():
                          "auto = p2p, falling back to nccl if peer mappings cannot be set up")
     ap.add_argument("--variant", type=int, default=0, help="aggregation kernel variant (0 auto, 1 shuffle, 2 bulk)")
     ap.add_argument("--edges-per-warp", type=int, default=0)
-    ap.add_argument("--drop-rate", type=float, default=0.5)
+    ap.add_argument("--drop-rate", type=float, default=0.0,
+                    help="both arms run DROP_RATE 0: the reference's in-place dropout trips libtorch 2.11's autograd "
+                         "version check (SURVEY 8c), so its CPU arm cannot run with dropout")
     ap.add_argument("--toolkit", default="gcn", choices=["gcn", "gcn_eager"],
                     help="gcn = toolkits/GCN.hpp order (aggregate, then GEMM: the headline config); gcn_eager = "
                          "toolkits/GCN_EAGER*.hpp order (GEMM, then aggregate the narrow result) - opt-in")
-    ap.add_argument("--cpu-sample-div", type=int, default=16, help="CPU baseline runs on E/div edges")
+    ap.add_argument("--cpu-sample-div", type=int, default=0,
+                    help="CPU arm runs a 1/div scale model of the workload (V/div vertices, E/div edges, same degree "
+                         "law, mean degree and widths); 0 = pick div from a probe so the run fits --cpu-budget-s")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own CUDA kernels")
@@ -111,15 +116,43 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # reference CPU arm (oracle/_ref/nts_ref_main = the reference's stock main.cpp + GCN_CPU.hpp, unmodified)
 # ---------------------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host threads this process may actually use: the scheduler affinity mask clipped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the lease: round 1's CPU arm ran 128 OpenMP threads on a fraction of
+    that and moved 4.6x between two boxes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:  # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:  # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
 def reference_cpu_epochs(V, layers, edges_u32, steps, warmup, threads=None):
     """Run ALGORITHM:GCNCPU of the unmodified reference on `edges_u32` ([E,2] numpy) for warmup+steps epochs and
     time epochs from its own per-epoch log lines.  Returns dict(value edges/s, s_per_epoch, cores, kind)."""
     import numpy as np
     binary = os.path.join(ROOT, "oracle", "_ref", "nts_ref_main")
-    cores = threads or os.cpu_count()
+    cores = threads or usable_cores()
     E = int(edges_u32.shape[0])
     if not os.path.exists(binary):
-        return _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores)
+        # never substitute the port silently: a "port" number must not be mistaken for the reference
+        raise SystemExit("bench.py: oracle/_ref/nts_ref_main is missing - build it with `make -C oracle ref` in the "
+                         "build container (it travels to the GPU box with the snapshot)")
     work = tempfile.mkdtemp(prefix="nts_bench_ref_")
     try:
         efile = os.path.join(work, "g.edge")
@@ -140,7 +173,8 @@ def reference_cpu_epochs(V, layers, edges_u32, steps, warmup, threads=None):
                 stamps.append(time.perf_counter())
         proc.wait()
         if proc.returncode != 0 or len(stamps) < warmup + steps:
-            return _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores)
+            raise SystemExit("bench.py: the reference CPU binary failed (rc %s, %d of %d epochs logged)" % (
+                proc.returncode, len(stamps), warmup + steps))
         # epoch k ends at stamps[k]; timed region = epochs warmup .. warmup+steps-1
         t = stamps[warmup + steps - 1] - stamps[warmup - 1] if warmup >= 1 else None
         if t is None:
@@ -161,7 +195,7 @@ def reference_cpu_op_level(V, layers, edges_u32, threads=None):
     binary = os.path.join(ROOT, "oracle", "_ref", "nts_ref_driver")
     if not os.path.exists(binary):
         return None
-    cores = threads or os.cpu_count()
+    cores = threads or usable_cores()
     work = tempfile.mkdtemp(prefix="nts_bench_refop_")
     out = {}
     try:
@@ -194,30 +228,6 @@ def reference_cpu_op_level(V, layers, edges_u32, threads=None):
         shutil.rmtree(work, ignore_errors=True)
 
 
-def _port_cpu_epochs(V, layers, edges_u32, steps, warmup, cores):
-    """Fallback when the reference binary is absent: the plain-C port of the aggregation loops (oracle/nts_oracle.c),
-    aggregation calls only (fwd F0, fwd F1, bwd F1)."""
-    import numpy as np
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_c
-    import nts_oracle as O
-    po = np.array([0, V], dtype=np.uint32)
-    c = O.build_chunks(edges_u32, V, po, 0)[0]
-    rng = np.random.default_rng(0)
-    xs = [rng.uniform(-1, 1, (V, f)).astype(np.float32) for f in layers[:-1]]
-    ts = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        for li, x in enumerate(xs):
-            oracle_c.segment_gather_sum(c.column_offset, c.row_indices, c.edge_weight_forward, x)
-            if li > 0:
-                oracle_c.segment_gather_sum(c.row_offset, c.column_indices, c.edge_weight_backward, x)
-        ts.append(time.perf_counter() - t0)
-    s = sum(ts[warmup:]) / steps
-    return {"value": 3.0 * edges_u32.shape[0] / s, "unit": "edges/s", "s_per_epoch": s, "cores": cores, "kind": "port"}
-
-
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -239,19 +249,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        div = max(1, args.cpu_sample_div)
-        edges = _sample_edges_cpu(V, E_rand, div)
-        res = reference_cpu_epochs(V, layers, edges, args.steps, args.warmup)
-        sample = "first 1/%d of the workload's random edges + all self loops (%d edges), all V, full widths" % (
-            div, edges.shape[0])
+        cores = usable_cores()
+        div, probe = pick_cpu_sample(V, E_rand, layers, args.cpu_sample_div, args.cpu_budget_s,
+                                     args.steps + args.warmup, cores)
+        Vs, edges = _scale_model(V, E_rand, div)
+        res = reference_cpu_epochs(Vs, layers, edges, args.steps, args.warmup, threads=cores)
+        sample = _sample_text(div, Vs, edges.shape[0], probe)
         line = {
             "impl": "reference", "metric": "gcn_aggregated_edges_per_sec", "value": res["value"], "unit": "edges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["s_per_epoch"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "epochs_per_sec": 1.0 / res["s_per_epoch"],
-            "config": {"workload": _workload_name(args.workload, V, E_total, layers), "sample": sample,
-                       "parallelism": "cpu x%d threads" % res["cores"]},
+            "config": _config(args, V, E_total, layers),
+            "run": {"parallelism": "unmodified reference ALGORITHM:GCNCPU, one process, %d host threads" % res["cores"]},
             "cpu_baseline": {"value": res["value"], "unit": "edges/s", "cores": res["cores"], "kind": res["kind"],
                              "sample": sample},
             "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -420,12 +431,24 @@ def main():
         # algorithmic bytes: E*(4 idx + 4 w + 4F row) + V_out*4F + (V_out+1)*4, summed over launches
         b_alg = k["edges"] * (8 + 4 * F0) + k["rows"] * 4 * F0 + (k["rows"] + k["calls"]) * 4
         achieved = b_alg / (k["ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "segment_gather_sum_kernel (fwd, F=%d)" % F0, "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                "traffic": _ncu_traffic() if (args.workload == "reddit" and world == 1 and args.zipf_s == 1.0
-                                              and not eager) else None,
+        t_launch = k["ms"] / k["calls"] * 1e-3
+        traffic = _ncu_traffic(F0) if (args.workload == "reddit" and world == 1 and args.zipf_s == 1.0
+                                       and not eager and ops._plan_mode != "off") else None
+        # compulsory traffic: every feature row once in, every output row once out, the graph arrays once
+        b_min = (k["rows"] * 4 * F0 * 2 + k["edges"] * 8 + (k["rows"] + k["calls"]) * 4) / k["calls"]
+        roof = {"bound": "hbm",
+                "kernel": ("planned_gather_sum_kernel" if ops._plan_mode != "off" else "segment_gather_sum_kernel") +
+                          " (fwd, F=%d)" % F0,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
+                "frac_note": "achieved = ALGORITHMIC bytes / time (SURVEY 8d: every gathered row counted as if it "
+                             "came from HBM); > 1 means L1/L2 reuse, it is NOT a physical HBM fraction - see "
+                             "frac_dram (ncu dram bytes of the same kernel / time) and frac_min (compulsory bytes)",
+                "traffic": traffic["bytes"] if traffic else None,
+                "traffic_source": traffic["source"] if traffic else None,
+                "frac_dram": (traffic["bytes"] / t_launch / 1e9 / peak) if traffic else None,
+                "frac_min": b_min / t_launch / 1e9 / peak,
                 "launches": k["calls"], "avg_ms_per_launch": k["ms"] / k["calls"],
-                "algorithmic_bytes_per_launch": b_alg / k["calls"]}
+                "algorithmic_bytes_per_launch": b_alg / k["calls"], "compulsory_bytes_per_launch": b_min}
     kernels = {"%s_F%d" % (tag, F): {"calls": d["calls"], "avg_ms": d["ms"] / d["calls"],
                                       "gedges_per_s": d["edges"] / (d["ms"] * 1e-3) / 1e9}
                for (tag, F), d in ksum.items()}
@@ -436,32 +459,38 @@ def main():
             ref_gpu = reference_gpu_kernels(pg, feats, layers, torch)
         except Exception as exc:  # baseline only: never fail the bench because of it
             ref_gpu = {"error": repr(exc)}
+    # ---- N > 1: parity of the distributed operator on THIS box, outside the timed regions
+    parity = multi_gpu_parity(pg, op_kwargs["exchange"], feats.detach(), layers, rank, world, dev) if world > 1 else None
     agg_ms = sum(d["ms"] for d in ksum.values()) / args.steps   # this rank's aggregation launches per step
     agg_only = {"ms_per_step": agg_ms, "edges_per_s": agg_calls * E_total / (agg_ms * 1e-3) if agg_ms > 0 else None,
                 "note": "CUDA-event time of the aggregation launches only (rank 0), SURVEY 8d"}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1 and not eager:   # the CPU arm is ALGORITHM:GCNCPU (gcn order)
-            div = max(1, args.cpu_sample_div)
-            edges = _sample_edges_cpu(V, E_rand, div)
-            r = reference_cpu_epochs(V, layers, edges, 2, 1)
+            cores = usable_cores()
+            div, probe = pick_cpu_sample(V, E_rand, layers, args.cpu_sample_div, min(args.cpu_budget_s, 25.0), 3, cores)
+            Vs, edges = _scale_model(V, E_rand, div)
+            r = reference_cpu_epochs(Vs, layers, edges, 2, 1, threads=cores)
             cpu = {"value": r["value"], "unit": "edges/s", "cores": r["cores"], "kind": r["kind"],
-                   "s_per_epoch": r["s_per_epoch"], "op_level": reference_cpu_op_level(V, layers, edges),
-                   "sample": "first 1/%d of the workload's random edges + all self loops (%d edges), all V, full "
-                             "widths; unmodified reference ALGORITHM:GCNCPU, 1 warm-up + 2 timed epochs" % (
-                                 div, edges.shape[0])}
+                   "s_per_epoch": r["s_per_epoch"], "op_level": reference_cpu_op_level(Vs, layers, edges, threads=cores),
+                   "sample": _sample_text(div, Vs, edges.shape[0], probe) +
+                             "; unmodified reference ALGORITHM:GCNCPU, 1 warm-up + 2 timed epochs"}
         line = {
             "metric": "gcn_aggregated_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "epochs_per_sec": 1e3 / ms_step,
-            "config": {"workload": _workload_name(args.workload, V, E_total, layers),
-                       "parallelism": "graph-partition x%d (reference partitioner), %s exchange" % (world, transport)
-                       if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (features %.0f MB, graph arrays %.0f MB per rank)" % (
-                           feats.numel() * 4 / 1e6, pg.owned_edges * 16 / 1e6),
-                       "drop_rate": args.drop_rate, "toolkit": args.toolkit,
-                       "aggregations_per_epoch": int(agg_calls), "kernel_variant": args.variant or 2, "zipf_s": args.zipf_s},
+            "config": _config(args, V, E_total, layers),
+            "run": {"parallelism": "graph-partition x%d (reference partitioner), %s exchange" % (world, transport)
+                    if world > 1 else "single GPU",
+                    "per_rank": "features %.0f MB, graph arrays %.0f MB" % (feats.numel() * 4 / 1e6,
+                                                                           pg.owned_edges * 16 / 1e6),
+                    "aggregation": "nts_gather_plan (measured slab count) for chunks >= 2^20 edges, plain kernel below"
+                    if ops._plan_mode != "off" else "plain kernel on the reference layout",
+                    "tape_note": "like the reference (core/ntsContext.hpp:283) the first graph op gets no backward "
+                                 "aggregation; unlike it, the dead input-layer dY = dH W^T GEMM is skipped too "
+                                 "(<2% of the epoch)"},
+            "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "kernels": kernels, "aggregation_only": agg_only, "reference_gpu_kernels": ref_gpu, "clocks": clocks,
         }
@@ -470,6 +499,64 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def multi_gpu_parity(pg, ex, feats, layers, rank, world, dev):
+    """ForwardGPUfuseOp forward + backward through the exchange engine actually benchmarked, against an fp64 reference
+    that shares nothing with it: 8 feature columns, the reference-layout chunk arrays (global ids), plain torch
+    index_add in float64, all-gather / all-reduce over NCCL for the rows other ranks own.  Per-ROW relative error
+    (max |err| of a row / max |truth| of that row); pass = 1e-4 (north_star).  The check the reference makes in
+    toolkits/test_getdepneighbor_gpu.hpp:184-328 (same inputs to both paths, forward and backward)."""
+    import torch
+    import torch.distributed as dist
+    from neutronstarlite_b200 import ops
+    C = 8
+    V = int(pg.partition_offset[-1])
+    lo, hi = int(pg.partition_offset[rank]), int(pg.partition_offset[rank + 1])
+    Vp = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(0x5EED0003 + rank)
+    g = torch.rand((Vp, layers[1]), generator=gen, device=dev) * 2 - 1
+    op = ops.ForwardGPUfuseOp(pg, None, exchange=ex)
+    y = op.forward(feats.contiguous())
+    dx = op.backward(g)
+    # global 8-column copies of X and (zero-padded) G
+    x8 = torch.zeros((V, C), dtype=torch.float64, device=dev)
+    x8[lo:hi] = feats[:, :C].double()
+    dist.all_reduce(x8)
+    y64 = torch.zeros((Vp, C), dtype=torch.float64, device=dev)
+    contrib = torch.zeros((V, C), dtype=torch.float64, device=dev)
+    g8 = g[:, :C].double()
+    rows = torch.arange(Vp, device=dev)
+    for c in pg.graph_chunks:
+        if not c.edge_size:
+            continue
+        co = c.column_offset_gpu.long()
+        dst = torch.repeat_interleave(rows, co[1:] - co[:-1])
+        src = c.row_indices_gpu.long()
+        y64.index_add_(0, dst, x8[src] * c.edge_weight_forward_gpu.double()[:, None])
+        ro = c.row_offset_gpu.long()
+        srcs = torch.repeat_interleave(torch.arange(c.src_range[0], c.src_range[1], device=dev), ro[1:] - ro[:-1])
+        dl = c.column_indices_gpu.long() - lo
+        contrib.index_add_(0, srcs, g8[dl] * c.edge_weight_backward_gpu.double()[:, None])
+        del dst, src, srcs, dl
+    dist.all_reduce(contrib)
+    dx64 = contrib[lo:hi]
+
+    def row_rel(a, t):
+        if not t.numel():
+            return 0.0
+        err = (a.double() - t).abs().amax(dim=1)
+        scale = t.abs().amax(dim=1).clamp(min=1e-30)
+        return float((err / scale).max().item())
+
+    worst = torch.tensor([row_rel(y[:, :C], y64), row_rel(dx[:, :C], dx64)], dtype=torch.float64, device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    fwd, bwd = float(worst[0].item()), float(worst[1].item())
+    return {"op": "ForwardGPUfuseOp forward (F=%d) + backward (F=%d) through the benchmarked exchange" % (
+                layers[0], layers[1]),
+            "reference": "float64 torch index_add on the reference-layout chunk arrays, %d columns, all %d ranks" % (C, world),
+            "max_row_rel_forward": fwd, "max_row_rel_backward": bwd, "max_rel": max(fwd, bwd), "tolerance": 1e-4,
+            "ok": bool(max(fwd, bwd) <= 1e-4)}
 
 
 def reference_gpu_kernels(pg, feats, layers, torch):
@@ -535,29 +622,71 @@ def reference_gpu_kernels(pg, feats, layers, torch):
     return out
 
 
+def _config(args, V, E_total, layers):
+    """The workload as both arms see it (identical dict in `ours` and `--impl reference`)."""
+    eager = args.toolkit == "gcn_eager"
+    n_layers = len(layers) - 1
+    return {"workload": _workload_name(args.workload, V, E_total, layers), "toolkit": args.toolkit,
+            "aggregations_per_epoch": 2 * n_layers if eager else 2 * n_layers - 1, "drop_rate": args.drop_rate,
+            "zipf_s": args.zipf_s,
+            "l2": "%s: features %.0f MB + graph arrays %.0f MB (all ranks), no flush between steps" % (
+                "inputs larger than L2" if V * layers[0] * 4 + E_total * 16 > 2 * 126e6 else
+                "inputs NOT larger than the 126 MB L2 (a test workload, not a bench line)",
+                V * layers[0] * 4 / 1e6, E_total * 16 / 1e6)}
+
+
+def _scale_model(V, E_rand, div):
+    """1/div scale model of the workload for the CPU arm: V/div vertices, E/div random edges of the same Zipf law
+    (so the mean degree, the skew and the feature widths are the workload's) + self loops.  [E,2] uint32."""
+    import numpy as np
+    import torch
+    from neutronstarlite_b200 import synth
+    Vs = max(1024, V // div)
+    src, dst = synth.zipf_edges(Vs, max(1, E_rand // div), torch.device("cpu"))
+    return Vs, torch.stack([src, dst], 1).numpy().astype(np.uint32)
+
+
+def pick_cpu_sample(V, E_rand, layers, div, budget_s, epochs, cores):
+    """div such that `epochs` epochs of the reference CPU GCN fit budget_s, from a probe at 1/64 scale (epoch time is
+    close to linear in the scale: aggregation ~ E, GEMMs ~ V).  div = 1 is the workload itself."""
+    if div and div > 0:
+        return int(div), None
+    pdiv = 64
+    Vp, edges = _scale_model(V, E_rand, pdiv)
+    r = reference_cpu_epochs(Vp, layers, edges, 1, 1, threads=cores)
+    full = r["s_per_epoch"] * pdiv
+    div = 1
+    while div < pdiv and full / div * epochs > budget_s:
+        div *= 2
+    return div, {"probe_div": pdiv, "probe_s_per_epoch": r["s_per_epoch"], "estimated_full_s_per_epoch": full}
+
+
+def _sample_text(div, Vs, Es, probe):
+    t = ("the workload itself (div 1)" if div == 1 else
+         "1/%d scale model of the workload: %d vertices, %d edges (same Zipf law, mean degree and widths)" % (div, Vs, Es))
+    if probe:
+        t += "; div chosen from a 1/%d probe (%.2f s/epoch -> %.0f s/epoch estimated at full size)" % (
+            probe["probe_div"], probe["probe_s_per_epoch"], probe["estimated_full_s_per_epoch"])
+    return t
+
+
 def _workload_name(name, V, E, layers):
     return "%s-shaped synthetic power-law graph: %d V, %d E (incl. self loops), 2-layer GCN %s fp32" % (
         name, V, E, "-".join(str(x) for x in layers))
 
 
-def _sample_edges_cpu(V, E_rand, div):
-    """The first 1/div of the workload's random edges + all self loops as a [E,2] uint32 numpy array, generated with
-    the same Zipf law on the CPU (the reference arm must not need a GPU)."""
-    import numpy as np
-    import torch
-    from neutronstarlite_b200 import synth
-    n = E_rand // div
-    src, dst = synth.zipf_edges(V, n, torch.device("cpu"))
-    return torch.stack([src, dst], 1).numpy().astype(np.uint32)
-
-
-def _ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def _ncu_traffic(F):
+    """dram bytes per call of the dominant kernel from the committed ncu capture of THIS round's kernel
+    (profiles/traffic.json: {"fwd_F602": {"bytes": ..., "kernel": ..., "source": ...}}), or None.  CUDA has no way to
+    read DRAM counters outside a profiler, so this is the one number of the line that is not measured live."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get("dram_bytes_per_launch_fwd_F602")
+        d = json.load(open(p)).get("fwd_F%d" % F)
+        if d and "planned_gather_sum_kernel" in d.get("kernel", ""):
+            return {"bytes": float(d["bytes"]), "source": d.get("source")}
     except Exception:
-        return None
+        pass
+    return None
 
 
 if __name__ == "__main__":

@@ -94,6 +94,46 @@ int nts_gather_by_src_from_dst(const float *input, float *output, const float *w
                                nts_vid_t dst_end, nts_vid_t edges, nts_vid_t batch_size,
                                nts_vid_t feature_size, int with_weight, void *stream);
 
+/* Row-range launch of the same contraction: `offsets` points at the first row of the range (offsets[0] ==
+ * edge_begin, offsets[n_rows] == edge_end), `output` at its first output row; indices / weight stay the whole
+ * arrays (addressed by absolute edge position).  Used by the exchange engine to aggregate the remote chunks in
+ * pipeline stages (core/graph.hpp:3678-3719 processes one chunk per ring step). */
+int nts_segment_gather_sum_range(const float *input, float *output, const float *weight, const nts_vid_t *indices,
+                                 const nts_vid_t *offsets, const nts_vid_t *slot_of, nts_vid_t index_base,
+                                 nts_vid_t n_rows, uint64_t edge_begin, uint64_t edge_end, nts_vid_t feature_size,
+                                 void *stream);
+
+/* ---- preprocessed aggregation: nts_gather_plan --------------------------------------------------------------------
+ * The arrays of one chunk direction (CSC: column_offset / row_indices / edge_weight_forward; CSR: row_offset /
+ * column_indices / edge_weight_backward; core/GraphSegment.h:52-139) regrouped ONCE on the device for repeated
+ * aggregation: edges bucketed by (slab of the gathered row, output row) with a stable sort so that one slab of the
+ * feature matrix stays L2-resident per launch, (row, weight) stored as interleaved pairs, gathers from 16-byte
+ * aligned (padded) rows.  The reference has no counterpart (its chunks are consumed as built); results equal
+ * nts_segment_gather_sum up to fp32 re-association across slabs.  `gather_rows` = rows of the gathered matrix
+ * (every mapped index must be < gather_rows); n_slabs = 0/1 disables the bucketing (pairs only).
+ * The plan owns copies of everything it needs: the input arrays may be released after create returns
+ * (create synchronises `stream`). */
+typedef struct nts_gather_plan nts_gather_plan;
+int nts_gather_plan_pick_slabs(nts_vid_t gather_rows, uint64_t n_edges, nts_vid_t n_rows, nts_vid_t feature_size,
+                               uint64_t l2_budget_bytes /* 0 = default */);
+nts_gather_plan *nts_gather_plan_create(const nts_vid_t *offsets, const nts_vid_t *indices, const float *weight,
+                                        const nts_vid_t *slot_of, nts_vid_t index_base, nts_vid_t n_rows,
+                                        uint64_t n_edges, nts_vid_t gather_rows, int n_slabs, void *stream);
+/* slab count chosen by MEASUREMENT on the real arrays at this feature width (candidates 1, 2, 4, ... built and timed
+ * once; hub-dominated graphs prefer no bucketing, uniform ones 8-16 slabs) */
+nts_gather_plan *nts_gather_plan_create_tuned(const nts_vid_t *offsets, const nts_vid_t *indices, const float *weight,
+                                              const nts_vid_t *slot_of, nts_vid_t index_base, nts_vid_t n_rows,
+                                              uint64_t n_edges, nts_vid_t gather_rows, nts_vid_t feature_size,
+                                              void *stream);
+int nts_gather_plan_destroy(nts_gather_plan *plan);
+int nts_gather_plan_slabs(const nts_gather_plan *plan);
+uint64_t nts_gather_plan_bytes(const nts_gather_plan *plan);
+/* output[r,:] += sum_e input[row(e),:] * w(e)   (accumulates; one launch per non-empty slab, in stream order) */
+int nts_gather_plan_run(nts_gather_plan *plan, const float *input, float *output, nts_vid_t feature_size,
+                        void *stream);
+int nts_gather_plan_last_launch(const nts_gather_plan *plan, int *launches, int *grid, int *k, int *u, int *outv);
+int nts_gather_plan_set_tuning(int u, int min_blocks, int edges_per_warp); /* measurement hook, 0 = default */
+
 /* Same contraction with the source row taken through a slot table instead of `index - base`:
  * row = slot_of[indices[e]].  Used with MirrorIndex (core/PartitionedGraph.hpp:295-305) for the fused
  * GAT aggregation, DistAggregateDstFuseWeight::forward (core/ntsDistCPUGraphOp.hpp:516-546), and with
@@ -251,12 +291,28 @@ int nts_signal_wait_geq(const uint32_t *flag, uint32_t value, void *stream);
 
 /* ---- the exchange engine: data plane of the distributed fused aggregation (peer-memory transport) ---------------------
  * Replaces Graph::sync_compute_decoupled / compute_sync_decoupled (core/graph.hpp:3455-3719) and the host-staged
- * NtsGraphCommunicator (comm/network.cpp:159-844).  The caller owns the CONTROL plane: it builds the plan arrays
- * (who needs which rows; neutronstarlite_b200/exchange.py::ExchangePlan documents them) and moves the two 64-byte IPC
- * handles per rank between processes (torch.distributed here, MPI in the reference's host code); the engine owns
- * windows, flags, streams, events and the launch sequence.  All pointers are device pointers that must outlive the
- * engine; per-partition arrays have `partitions` entries (own entry ignored). */
+ * NtsGraphCommunicator (comm/network.cpp:159-844).  PUSH model over CUDA-IPC windows, one pipeline stage per source
+ * partition in the reference's ring order (core/graph.hpp:3678-3683): the owner of a row stores it straight into the
+ * reader's receive window over NVLink and raises an epoch flag; the reader aggregates chunk (p+s) as soon as the rows
+ * of partition (p+s) have landed (csrc/nts_exchange.cu documents the protocol).
+ * The caller owns the CONTROL plane: it builds the plan arrays (who needs which rows;
+ * neutronstarlite_b200/exchange.py::ExchangePlan or nts_exchange_plan_* below) and moves the two 64-byte IPC handles
+ * per rank between processes (torch.distributed here, MPI in the reference's host code); the engine owns windows,
+ * flags, streams, events and the launch sequence.  All pointers are device pointers that must outlive the engine;
+ * per-partition arrays have `partitions` entries (own entry ignored).  Row layouts ("partition order"): the receive
+ * staging of rank r holds the rows it reads from partition 0, 1, ... (r skipped), need_count[i] rows each; the
+ * gradient staging holds what ranks 0, 1, ... (r skipped) return, send_count[j] rows each = the order of
+ * send_rows_all. */
 typedef struct nts_exchange nts_exchange;
+typedef struct nts_exchange_chunk {          /* remote chunk i: sources in partition i -> my destinations */
+  const nts_vid_t *column_offset;            /* [V_p+1]  graph_chunks[i]->column_offset_gpu */
+  const nts_vid_t *slots;                    /* [E_i]    row_indices remapped to 0..need_count[i]-1 (rank in need list) */
+  const float *weight_forward;               /* [E_i]    graph_chunks[i]->edge_weight_forward_gpu */
+  const nts_vid_t *row_offset_compact;       /* [need_count[i]+1] row_offset restricted to the active sources */
+  const nts_vid_t *column_indices;           /* [E_i]    graph_chunks[i]->column_indices_gpu (global destination ids) */
+  const float *weight_backward;              /* [E_i]    graph_chunks[i]->edge_weight_backward_gpu */
+  uint64_t edges;
+} nts_exchange_chunk;
 typedef struct nts_exchange_desc {
   int partitions, rank;
   nts_vid_t owned_vertices, dst_start;      /* V_p and partition_offset[rank] */
@@ -264,29 +320,30 @@ typedef struct nts_exchange_desc {
   const nts_vid_t *local_column_offset, *local_row_indices, *local_row_offset, *local_column_indices;
   const float *local_weight_forward, *local_weight_backward;
   nts_vid_t local_edges;
-  /* all remote chunks merged: CSC whose indices are slots of the receive staging buffer ... */
-  const nts_vid_t *remote_column_offset, *remote_slots;
-  const float *remote_weight;
-  uint64_t remote_edges;
-  /* ... and compact CSR over the active sources (rows = send-staging layout) */
-  const nts_vid_t *backward_offsets, *backward_indices;
-  const float *backward_weight;
-  nts_vid_t recv_total, send_total;         /* rows I read from peers / rows peers read from me */
-  const nts_vid_t *need_count;              /* [P] rows of partition i that I read */
-  const nts_vid_t *const *need;             /* [P] device lists: local ids (within partition i) of those rows */
-  const nts_vid_t *send_count;              /* [P] rows of mine that peer j reads */
-  const nts_vid_t *send_rows_all;           /* device: concatenation over peers j != rank of those rows */
-  const nts_vid_t *peer_bwd_offset;         /* [P] row offset of MY slice inside peer j's backward window */
+  const nts_exchange_chunk *chunks;         /* [P] remote chunks (host array of device pointers) */
+  const nts_vid_t *need_count;              /* [P] rows of partition i that I read (= active sources of chunk i) */
+  const nts_vid_t *send_count;              /* [P] rows of mine that rank j reads */
+  const nts_vid_t *send_rows_all;           /* device: concatenation over j != rank (ascending) of those local row ids */
+  const nts_vid_t *fwd_push_offset;         /* [P] first row of MY rows inside rank j's receive staging */
+  const nts_vid_t *bwd_push_offset;         /* [P] first row of MY partials inside rank i's gradient staging */
 } nts_exchange_desc;
 
 nts_exchange *nts_exchange_create(const nts_exchange_desc *desc);
 int nts_exchange_destroy(nts_exchange *ex);
+/* floats ONE epoch buffer of the receive window needs at this width; take the MAX over ranks before reserving */
 uint64_t nts_exchange_required_floats(const nts_exchange *ex, nts_vid_t feature_size);
-/* grow the exported window; *reallocated = 1 means: exchange handles again and call nts_exchange_open_peers */
-int nts_exchange_reserve(nts_exchange *ex, uint64_t floats, int *reallocated);
+uint64_t nts_exchange_capacity_floats(const nts_exchange *ex);
+/* Replacing the exported window is COLLECTIVE and must not race with peers that still map or write it.  On every
+ * rank: nts_exchange_release_peers (drains this rank's device work, closes its mappings of the peers' windows) ->
+ * barrier -> nts_exchange_reserve (frees / allocates; n_buffers = 2 lets a rank run one exchange ahead of a slow
+ * peer, 1 halves the memory) -> nts_exchange_handles -> all-gather of the handles -> nts_exchange_open_peers ->
+ * barrier.  Reserve once for the widest layer to keep cudaMalloc out of the epoch loop. */
+int nts_exchange_release_peers(nts_exchange *ex);
+int nts_exchange_reserve(nts_exchange *ex, uint64_t floats_per_buffer, int n_buffers);
 int nts_exchange_handles(nts_exchange *ex, unsigned char window_handle[64], unsigned char flags_handle[64]);
 int nts_exchange_open_peers(nts_exchange *ex, const unsigned char *window_handles, const unsigned char *flag_handles);
-/* Y_p += sum_i A_{p<-i} X_i  (ForwardGPUfuseOp::forward, core/ntsDistGPUFusedGraphOp.hpp:56-73); y zeroed by caller */
+/* Y_p += sum_i A_{p<-i} X_i  (ForwardGPUfuseOp::forward, core/ntsDistGPUFusedGraphOp.hpp:56-73); y zeroed by caller.
+ * Every rank must issue the same sequence of forward / backward calls (SPMD, like the reference's ring). */
 int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t feature_size, void *stream);
 /* dX_p += sum_j A_{j<-p}^T dY_j (ForwardGPUfuseOp::backward, :75-90); dx zeroed by caller */
 int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t feature_size, void *stream);
@@ -298,7 +355,9 @@ int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t
  * column_offset[V_p+1] / row_indices[E_i] (global source ids) / edge_weight_forward, row_offset[V_i+1] /
  * column_indices[E_i] (global destination ids) / edge_weight_backward, src_range, dst_range, edge_size.
  * Sequence:  create -> pack_needs -> (caller moves every rank's pack to every rank) -> set_peer_needs for each
- * peer -> finalize -> create_from_plan (uploads; the plan owns the device copies and must outlive the engine). */
+ * peer -> finalize -> create_from_plan (uploads; the plan owns the device copies and must outlive the engine).
+ * The merged arrays of the view (one CSC / one compact CSR over all remote chunks) serve transports that aggregate
+ * all remote chunks in one launch (the NCCL all-to-all path); the peer-memory engine works per chunk. */
 typedef struct nts_host_chunk {
   const nts_vid_t *column_offset, *row_indices, *row_offset, *column_indices;
   const float *edge_weight_forward, *edge_weight_backward;
@@ -323,6 +382,7 @@ typedef struct nts_exchange_plan_view {
   nts_vid_t owned_vertices, recv_total, send_total, backward_rows;
   uint64_t remote_edges;
   const nts_vid_t *need_count, *send_count, *peer_bwd_offset;   /* [P] each */
+  const nts_vid_t *fwd_push_offset, *bwd_push_offset;           /* [P] each, see nts_exchange_desc */
   const nts_vid_t *remote_column_offset, *remote_slots;         /* [V_p+1], [remote_edges] */
   const float *remote_weight;
   const nts_vid_t *backward_offsets, *backward_indices;         /* [backward_rows+1], [remote_edges] */
@@ -330,11 +390,17 @@ typedef struct nts_exchange_plan_view {
   const nts_vid_t *send_rows_all;                               /* [send_total] */
 } nts_exchange_plan_view;
 int nts_exchange_plan_get_view(const nts_exchange_plan *plan, nts_exchange_plan_view *view);
-/* the six pointers are the DEVICE arrays of the local chunk graph_chunks[rank] (CopyGraphToDevice) */
-nts_exchange *nts_exchange_create_from_plan(nts_exchange_plan *plan, const nts_vid_t *local_column_offset,
-                                            const nts_vid_t *local_row_indices, const float *local_weight_forward,
-                                            const nts_vid_t *local_row_offset, const nts_vid_t *local_column_indices,
-                                            const float *local_weight_backward);
+/* per remote chunk i of the finalized plan (host arrays, live as long as the plan): row_indices as ranks in the need
+ * list [E_i], row_offset restricted to the active sources [need_count[i]+1] */
+int nts_exchange_plan_chunk(const nts_exchange_plan *plan, int i, const nts_vid_t **slots,
+                            const nts_vid_t **row_offset_compact);
+/* DEVICE arrays of CSC_segment_pinned graph_chunks[i] as uploaded by CopyGraphToDevice (core/GraphSegment.cpp:178-220),
+ * one entry per source partition; the plan uploads the derived arrays itself and must outlive the engine */
+typedef struct nts_device_chunk {
+  const nts_vid_t *column_offset, *row_indices, *row_offset, *column_indices;
+  const float *edge_weight_forward, *edge_weight_backward;
+} nts_device_chunk;
+nts_exchange *nts_exchange_create_from_plan(nts_exchange_plan *plan, const nts_device_chunk *device_chunks);
 
 /* ---- host-side graph preparation (C++ with OpenMP; no device involved) -----------------------------------
  * Restates the layout contract of core/graph.hpp:1185-1211 (partitioner), :4396-4401 (degree clamp),

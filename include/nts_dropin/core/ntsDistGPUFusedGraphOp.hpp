@@ -2,8 +2,8 @@
 // (constructor, forward, backward as toolkits/GCN.hpp:217-235 and core/ntsContext.hpp:108-129 use them), with the
 // host-staged exchange of the original - `.cpu()` of the features, emit_buffer, MPI_Send / MPI_Recv of (vid,row)
 // records, zero-copy reads of pinned host memory (core/graph.hpp:3455-3719, comm/network.cpp:159-844) - replaced by
-// the device-resident peer-memory exchange of libnts_b200 (nts_exchange_*: CUDA-IPC windows over NVLink, one merged
-// aggregation launch for all remote chunks).
+// the device-resident peer-memory exchange of libnts_b200 (nts_exchange_*: rows pushed into CUDA-IPC windows over NVLink,
+// one pipeline stage per source partition).
 //
 // How a maintainer wires it in: replace the body of core/ntsDistGPUFusedGraphOp.hpp by an #include of this file, or
 // - without touching the tree, which is what oracle/Makefile does - compile with
@@ -19,7 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
-#include <set>
+#include <algorithm>
 #include <vector>
 
 #include <mpi.h>
@@ -57,30 +57,34 @@ public:
     return *e;
   }
 
-  // collective on first use of a feature width: size the exported window on every rank, swap IPC handles
+  // Collective whenever a feature width needs a larger receive window than every rank holds (all ranks keep the same
+  // capacity: the max over ranks).  Follows the contract of nts_exchange_reserve (nts_b200.h): release -> barrier ->
+  // reallocate -> swap IPC handles -> open -> barrier.  Reserving for the widest layer first (max_layer) keeps
+  // cudaMalloc out of the epoch loop.
   void reserve(int feature_size) {
-    if (reserved_.count(feature_size))
+    if (feature_size <= max_feature_)
       return;
+    max_feature_ = feature_size;
     unsigned long need = (unsigned long)nts_exchange_required_floats(engine_, (nts_vid_t)feature_size), all = 0;
     MPI_Allreduce(&need, &all, 1, MPI_UNSIGNED_LONG, MPI_MAX, MPI_COMM_WORLD);
-    int realloc = 0, any = 0;
-    if (nts_exchange_reserve(engine_, all, &realloc))
+    if (all <= (unsigned long)nts_exchange_capacity_floats(engine_))
+      return;
+    if (nts_exchange_release_peers(engine_))
+      die("nts_exchange_release_peers");
+    MPI_Barrier(MPI_COMM_WORLD); // nobody maps or writes the old windows any more
+    if (nts_exchange_reserve(engine_, all, 2))
       die("nts_exchange_reserve");
-    MPI_Allreduce(&realloc, &any, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
-    if (any) {
-      std::vector<unsigned char> windows((size_t)P_ * NTS_IPC_HANDLE_BYTES), flags((size_t)P_ * NTS_IPC_HANDLE_BYTES);
-      if (nts_exchange_handles(engine_, windows.data() + (size_t)rank_ * NTS_IPC_HANDLE_BYTES,
-                               flags.data() + (size_t)rank_ * NTS_IPC_HANDLE_BYTES))
-        die("nts_exchange_handles");
-      for (int r = 0; r < P_; r++) {
-        bcast_bytes(windows.data() + (size_t)r * NTS_IPC_HANDLE_BYTES, NTS_IPC_HANDLE_BYTES, r);
-        bcast_bytes(flags.data() + (size_t)r * NTS_IPC_HANDLE_BYTES, NTS_IPC_HANDLE_BYTES, r);
-      }
-      if (nts_exchange_open_peers(engine_, windows.data(), flags.data()))
-        die("nts_exchange_open_peers");
-      MPI_Barrier(MPI_COMM_WORLD);
+    std::vector<unsigned char> windows((size_t)P_ * NTS_IPC_HANDLE_BYTES), flags((size_t)P_ * NTS_IPC_HANDLE_BYTES);
+    if (nts_exchange_handles(engine_, windows.data() + (size_t)rank_ * NTS_IPC_HANDLE_BYTES,
+                             flags.data() + (size_t)rank_ * NTS_IPC_HANDLE_BYTES))
+      die("nts_exchange_handles");
+    for (int r = 0; r < P_; r++) {
+      bcast_bytes(windows.data() + (size_t)r * NTS_IPC_HANDLE_BYTES, NTS_IPC_HANDLE_BYTES, r);
+      bcast_bytes(flags.data() + (size_t)r * NTS_IPC_HANDLE_BYTES, NTS_IPC_HANDLE_BYTES, r);
     }
-    reserved_.insert(feature_size);
+    if (nts_exchange_open_peers(engine_, windows.data(), flags.data()))
+      die("nts_exchange_open_peers");
+    MPI_Barrier(MPI_COMM_WORLD);
   }
 
   nts_exchange *engine() { return engine_; }
@@ -128,18 +132,26 @@ private:
     }
     if (nts_exchange_plan_finalize(plan_))
       die("nts_exchange_plan_finalize");
-    CSC_segment_pinned *mine = pg->graph_chunks[rank_];
-    engine_ = nts_exchange_create_from_plan(plan_, mine->column_offset_gpu, mine->row_indices_gpu,
-                                            mine->edge_weight_forward_gpu, mine->row_offset_gpu,
-                                            mine->column_indices_gpu, mine->edge_weight_backward_gpu);
+    std::vector<nts_device_chunk> dc(P_); // what CopyGraphToDevice uploaded for every chunk
+    for (int i = 0; i < P_; i++) {
+      CSC_segment_pinned *c = pg->graph_chunks[i];
+      dc[i].column_offset = c->column_offset_gpu;
+      dc[i].row_indices = c->row_indices_gpu;
+      dc[i].row_offset = c->row_offset_gpu;
+      dc[i].column_indices = c->column_indices_gpu;
+      dc[i].edge_weight_forward = c->edge_weight_forward_gpu;
+      dc[i].edge_weight_backward = c->edge_weight_backward_gpu;
+    }
+    engine_ = nts_exchange_create_from_plan(plan_, dc.data());
     if (!engine_)
       die("nts_exchange_create_from_plan");
+    reserve(std::max(1, (int)g->gnnctx->max_layer)); // widest layer of LAYERS (core/graph.hpp:310-311)
   }
 
   int P_ = 1, rank_ = 0;
   nts_exchange_plan *plan_ = nullptr;
   nts_exchange *engine_ = nullptr;
-  std::set<int> reserved_;
+  int max_feature_ = 0;
 };
 
 } // namespace b200

@@ -48,6 +48,16 @@ SIGNATURES = {
     "nts_segment_gather_sum": (_int, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u64, _u32, _vp]),
     "nts_gather_by_dst_from_src": (_int, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _int, _vp]),
     "nts_gather_by_src_from_dst": (_int, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _int, _vp]),
+    "nts_segment_gather_sum_range": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u64, _u64, _u32, _vp]),
+    "nts_gather_plan_pick_slabs": (_int, [_u32, _u64, _u32, _u32, _u64]),
+    "nts_gather_plan_create": (_vp, [_vp, _vp, _vp, _vp, _u32, _u32, _u64, _u32, _int, _vp]),
+    "nts_gather_plan_create_tuned": (_vp, [_vp, _vp, _vp, _vp, _u32, _u32, _u64, _u32, _u32, _vp]),
+    "nts_gather_plan_destroy": (_int, [_vp]),
+    "nts_gather_plan_slabs": (_int, [_vp]),
+    "nts_gather_plan_bytes": (_u64, [_vp]),
+    "nts_gather_plan_run": (_int, [_vp, _vp, _vp, _u32, _vp]),
+    "nts_gather_plan_last_launch": (_int, [_vp] + [C.POINTER(_int)] * 5),
+    "nts_gather_plan_set_tuning": (_int, [_int, _int, _int]),
     "nts_segment_gather_sum_slots": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u64, _u32, _vp]),
     "nts_segment_gather_sum_heads": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u64, _u32, _u32, _vp]),
     "nts_aggregate_set_variant": (_int, [_int, _int]),
@@ -85,6 +95,14 @@ SIGNATURES = {
 
 
 
+class ExchangeChunk(C.Structure):
+    """nts_exchange_chunk of include/nts_b200.h (device arrays of one remote chunk)."""
+    _fields_ = [
+        ("column_offset", _vp), ("slots", _vp), ("weight_forward", _vp), ("row_offset_compact", _vp),
+        ("column_indices", _vp), ("weight_backward", _vp), ("edges", _u64),
+    ]
+
+
 class ExchangeDesc(C.Structure):
     """nts_exchange_desc of include/nts_b200.h."""
     _fields_ = [
@@ -92,11 +110,17 @@ class ExchangeDesc(C.Structure):
         ("local_column_offset", _vp), ("local_row_indices", _vp), ("local_row_offset", _vp),
         ("local_column_indices", _vp), ("local_weight_forward", _vp), ("local_weight_backward", _vp),
         ("local_edges", _u32),
-        ("remote_column_offset", _vp), ("remote_slots", _vp), ("remote_weight", _vp), ("remote_edges", _u64),
-        ("backward_offsets", _vp), ("backward_indices", _vp), ("backward_weight", _vp),
-        ("recv_total", _u32), ("send_total", _u32),
-        ("need_count", C.POINTER(_u32)), ("need", C.POINTER(_vp)), ("send_count", C.POINTER(_u32)),
-        ("send_rows_all", _vp), ("peer_bwd_offset", C.POINTER(_u32)),
+        ("chunks", C.POINTER(ExchangeChunk)),
+        ("need_count", C.POINTER(_u32)), ("send_count", C.POINTER(_u32)),
+        ("send_rows_all", _vp), ("fwd_push_offset", C.POINTER(_u32)), ("bwd_push_offset", C.POINTER(_u32)),
+    ]
+
+
+class DeviceChunk(C.Structure):
+    """nts_device_chunk of include/nts_b200.h."""
+    _fields_ = [
+        ("column_offset", _vp), ("row_indices", _vp), ("row_offset", _vp), ("column_indices", _vp),
+        ("edge_weight_forward", _vp), ("edge_weight_backward", _vp),
     ]
 
 
@@ -104,7 +128,9 @@ SIGNATURES.update({
     "nts_exchange_create": (_vp, [C.POINTER(ExchangeDesc)]),
     "nts_exchange_destroy": (_int, [_vp]),
     "nts_exchange_required_floats": (_u64, [_vp, _u32]),
-    "nts_exchange_reserve": (_int, [_vp, _u64, C.POINTER(_int)]),
+    "nts_exchange_capacity_floats": (_u64, [_vp]),
+    "nts_exchange_release_peers": (_int, [_vp]),
+    "nts_exchange_reserve": (_int, [_vp, _u64, _int]),
     "nts_exchange_handles": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "nts_exchange_open_peers": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "nts_exchange_forward": (_int, [_vp, _vp, _vp, _u32, _vp]),
@@ -129,6 +155,7 @@ class ExchangePlanView(C.Structure):
         ("owned_vertices", _u32), ("recv_total", _u32), ("send_total", _u32), ("backward_rows", _u32),
         ("remote_edges", _u64),
         ("need_count", C.POINTER(_u32)), ("send_count", C.POINTER(_u32)), ("peer_bwd_offset", C.POINTER(_u32)),
+        ("fwd_push_offset", C.POINTER(_u32)), ("bwd_push_offset", C.POINTER(_u32)),
         ("remote_column_offset", C.POINTER(_u32)), ("remote_slots", C.POINTER(_u32)),
         ("remote_weight", C.POINTER(C.c_float)),
         ("backward_offsets", C.POINTER(_u32)), ("backward_indices", C.POINTER(_u32)),
@@ -146,7 +173,8 @@ SIGNATURES.update({
     "nts_exchange_plan_set_peer_needs": (_int, [_vp, _int, _vp, _vp]),
     "nts_exchange_plan_finalize": (_int, [_vp]),
     "nts_exchange_plan_get_view": (_int, [_vp, C.POINTER(ExchangePlanView)]),
-    "nts_exchange_create_from_plan": (_vp, [_vp] * 7),
+    "nts_exchange_plan_chunk": (_int, [_vp, _int, C.POINTER(C.POINTER(_u32)), C.POINTER(C.POINTER(_u32))]),
+    "nts_exchange_create_from_plan": (_vp, [_vp, C.POINTER(DeviceChunk)]),
 })
 
 _lib = None

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
                               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
                               const uint32_t *__restrict__ slot_of, uint32_t base, uint32_t n_rows,
                               uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
-                              uint32_t tile_major, uint32_t heads, AttParams att) {
+                              uint32_t tile_major, uint32_t heads, AttParams att, uint32_t e_begin, uint32_t out_mod) {
   static_assert(!(HM == 1 && BULK), "[E, H] weight matrices are not bulk-staged (indices of HM 0 / 2 are)");
   using V = typename Vec<VEC>::type;
   const uint32_t n_edges = (uint32_t)n_edges64;
@@ -171,11 +171,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   //     touch one column slab of the feature matrix, which is sized to stay resident in the 126 MB L2.
   //     Warps per tile are padded to a multiple of the CTA size so a CTA never straddles two tiles.
   const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp_in_block;
-  const uint64_t n_quanta = (n_edges64 + Q - 1) / Q;
+  // the launch covers edges [e_begin, n_edges64) of the arrays (e_begin = off[0]; 0 except for row-range launches)
+  const uint64_t n_quanta = (n_edges64 - e_begin + Q - 1) / Q;
   const uint64_t wpt = (n_quanta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock;
   const uint32_t tile = tile_major ? (uint32_t)(gwarp / wpt) : (uint32_t)(gwarp % tiles);
   const uint64_t q = tile_major ? gwarp % wpt : gwarp / tiles;
-  const uint64_t e0_64 = q * (uint64_t)Q;
+  const uint64_t e0_64 = e_begin + q * (uint64_t)Q;
 
   // BULK staging buffers: indices+weights of every edge this CTA touches
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -188,8 +189,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     const uint64_t cta_w0 = (uint64_t)blockIdx.x * kWarpsPerBlock;
     const uint64_t first_q = tile_major ? cta_w0 % wpt : cta_w0 / tiles;
     const uint64_t last_q = tile_major ? first_q + kWarpsPerBlock - 1 : (cta_w0 + kWarpsPerBlock - 1) / tiles;
-    uint64_t ce0 = first_q * (uint64_t)Q;
-    uint64_t ce1 = (last_q + 1) * (uint64_t)Q;
+    uint64_t ce0 = e_begin + first_q * (uint64_t)Q;
+    uint64_t ce1 = e_begin + (last_q + 1) * (uint64_t)Q;
     if (ce1 > n_edges)
       ce1 = n_edges;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     if constexpr (HM == 2) {
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        const size_t o = (size_t)row * heads + hk[k];
+        const size_t o = (size_t)(out_mod ? row % out_mod : row) * heads + hk[k];
         att_d[k] = __ldg(att.d + o);
         att_m[k] = __ldg(att.m + o);
         att_iz[k] = 1.f / __ldg(att.z + o);
@@ -263,8 +264,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   };
   load_att_row();
 
+  // slab-bucketed launches (out_mod != 0): `row` is a virtual row (slab * out_mod + output row); the slabs of one
+  // output row are processed by different warps, possibly at the same time, so every flush is a reduction
   auto flush = [&](bool whole) {
-    V *o = reinterpret_cast<V *>(out + (size_t)row * F) + c0;
+    const uint32_t orow = out_mod ? row % out_mod : row;
+    whole = whole && !out_mod;
+    V *o = reinterpret_cast<V *>(out + (size_t)orow * F) + c0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
       if (act[k]) {
@@ -394,6 +399,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 struct LaunchShape {
   int vec, k, u, minb;
   uint32_t tiles, tile_vecs, tile_major, heads;
+  uint32_t e_begin = 0; // first edge of the launch (row-range launches), offsets[0]
+  uint32_t out_mod = 0; // != 0: offsets index virtual rows slab * out_mod + row (slab-bucketed arrays)
 };
 
 static LaunchShape pick_shape(const float *in, const float *out, uint32_t F, uint32_t heads) {
@@ -454,7 +461,7 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
                         const uint32_t *idx, const uint32_t *off, const uint32_t *slot_of, uint32_t base,
                         uint32_t n_rows, uint64_t n_edges, uint32_t F, uint32_t Q, cudaStream_t st,
                         const AttParams *att = nullptr) {
-  const uint64_t quanta = (n_edges + Q - 1) / Q;
+  const uint64_t quanta = (n_edges - sh.e_begin + Q - 1) / Q;
   uint64_t warps;
   if (sh.tile_major)
     warps = (quanta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock * sh.tiles;
@@ -475,15 +482,15 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
         g_last_smem = (int)smem;
         kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, nullptr, idx, off, slot_of, base, n_rows,
                                                                   n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
-                                                                  sh.heads, *att);
+                                                                  sh.heads, *att, sh.e_begin, sh.out_mod);
       } else if (att)
         segment_gather_sum_kernel<VEC, K, U, false, 1, 2><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
             in, out, nullptr, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
-            sh.heads, *att);
+            sh.heads, *att, sh.e_begin, sh.out_mod);
       else
         segment_gather_sum_kernel<VEC, K, U, false, 1, 1><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
             in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major,
-            sh.heads, kNoAtt);
+            sh.heads, kNoAtt, sh.e_begin, sh.out_mod);
       NTS_LAUNCH_CHECK();
       return 0;
     } else {
@@ -497,12 +504,13 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
     NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     g_last_smem = (int)smem;
     kern<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(in, out, w, idx, off, slot_of, base, n_rows, n_edges, F,
-                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major, 1u, kNoAtt);
+                                                              Q, sh.tiles, sh.tile_vecs, sh.tile_major, 1u, kNoAtt, sh.e_begin,
+                                                              sh.out_mod);
   } else {
     g_last_smem = 0;
     segment_gather_sum_kernel<VEC, K, U, false, MINB><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(
         in, out, w, idx, off, slot_of, base, n_rows, n_edges, F, Q, sh.tiles, sh.tile_vecs, sh.tile_major, 1u,
-        kNoAtt);
+        kNoAtt, sh.e_begin, sh.out_mod);
   }
   NTS_LAUNCH_CHECK();
   return 0;
@@ -514,8 +522,10 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
 
 static int segment_gather_sum(const float *in, float *out, const float *w, const uint32_t *idx, const uint32_t *off,
                               const uint32_t *slot_of, uint32_t base, uint32_t n_rows, uint64_t n_edges, uint32_t F,
-                              cudaStream_t st, uint32_t heads = 1, const AttParams *att = nullptr) {
-  if (n_rows == 0 || n_edges == 0 || F == 0)
+                              cudaStream_t st, uint32_t heads = 1, const AttParams *att = nullptr,
+                              uint64_t e_begin = 0, uint32_t out_mod = 0) {
+  // n_edges is the END of the edge range [e_begin, n_edges) (= the edge count for whole-array launches)
+  if (n_rows == 0 || n_edges <= e_begin || F == 0)
     return 0;
   NTS_ARG_CHECK(in && out && idx && off, "null pointer passed to segment_gather_sum");
   NTS_ARG_CHECK(n_edges < 0xffffffffull, "chunk edge count must fit uint32 offsets");
@@ -524,6 +534,8 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
     NTS_ARG_CHECK(F % heads == 0, "feature_size must be a multiple of heads");
   }
   LaunchShape s = pick_shape(in, out, F, heads);
+  s.e_begin = (uint32_t)e_begin;
+  s.out_mod = out_mod;
   if (heads > 1 || att) { // per-head kernels: untuned occupancy point
     s.minb = 1;
     int budget = 40 / (s.k * s.vec);
@@ -533,7 +545,7 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
   uint32_t Q = g_edges_per_warp > 0 ? (uint32_t)g_edges_per_warp : 512u;
   if (g_edges_per_warp <= 0) {
     const uint64_t want_warps = (uint64_t)sm_count() * 64;
-    while (Q > 32 && ((n_edges + Q - 1) / Q) * s.tiles < want_warps)
+    while (Q > 32 && ((n_edges - e_begin + Q - 1) / Q) * s.tiles < want_warps)
       Q >>= 1;
   }
   Q = (Q + 31u) & ~31u;
@@ -592,6 +604,15 @@ int nts_segment_gather_sum(const float *input, float *output, const float *weigh
                            nts_vid_t feature_size, void *stream) {
   return nts::segment_gather_sum(input, output, weight, indices, offsets, nullptr, index_base, n_rows, n_edges,
                                  feature_size, nts::as_stream(stream));
+}
+
+int nts_segment_gather_sum_range(const float *input, float *output, const float *weight, const nts_vid_t *indices,
+                                 const nts_vid_t *offsets, const nts_vid_t *slot_of, nts_vid_t index_base,
+                                 nts_vid_t n_rows, uint64_t edge_begin, uint64_t edge_end, nts_vid_t feature_size,
+                                 void *stream) {
+  NTS_ARG_CHECK(edge_begin <= edge_end, "edge range is reversed");
+  return nts::segment_gather_sum(input, output, weight, indices, offsets, slot_of, index_base, n_rows, edge_end,
+                                 feature_size, nts::as_stream(stream), 1, nullptr, edge_begin, 0);
 }
 
 int nts_segment_gather_sum_slots(const float *input, float *output, const float *weight, const nts_vid_t *indices,

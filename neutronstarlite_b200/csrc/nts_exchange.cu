@@ -2,62 +2,190 @@
 //
 // Replaces the GPU drivers of the reference engine - Graph::sync_compute_decoupled (forward, core/graph.hpp:3639-3719)
 // and Graph::compute_sync_decoupled (backward, :3455-3622) - and the host-staged NtsGraphCommunicator they drive
-// (comm/network.cpp:159-844) for the peer-memory ("p2p") transport:
+// (comm/network.cpp:159-844).  Peer-memory ("p2p") transport, PUSH model, pipelined per source partition like the
+// reference's ring (aggregate chunk (p+s) while chunk (p+s+1) is in flight, core/graph.hpp:3678-3719):
 //
-//   forward   publish my rows in a CUDA-IPC window -> aggregate the local chunk while the receiver side PULLS the rows
-//             it needs out of every peer's window over NVLink (nts_gather_rows on mapped peer pointers, side stream)
-//             -> ONE launch over the merged CSC of all remote chunks.
-//   backward  ONE launch computes the partial gradients of the active sources of all remote chunks straight into my
-//             window -> publish -> local chunk while the slices the peers computed for me are copied out of their
-//             windows -> one scatter-add.
+//   forward   ONE persistent kernel on a high-priority side stream gathers, for every peer j in ring order
+//             (p-1, p-2, ...), the rows of X_p that j reads and STORES them straight into j's receive window over
+//             NVLink (CUDA-IPC mapping; no window copy of X, no packing pass), then raises pushed[p] in j's flags.
+//             Meanwhile the main stream aggregates the local chunk and then, for s = 1..P-1, waits for the flag of
+//             partition (p+s) and aggregates chunk (p+s) from its slice of the receive window.
+//   backward  per remote chunk (p+s): partial gradients of its active sources (compact CSR) into a local staging
+//             slice, which the side stream pushes into the owner's window as soon as that launch has finished;
+//             the local chunk overlaps with the pushes; one scatter-add of everything received.
 //
-// Cross-GPU ordering: epoch-numbered flags in peer memory (published[rank], consumed[rank][peer]) written / awaited by
-// tiny kernels with release / acquire semantics at system scope; everything else is stream order + two events.
-// The CONTROL plane (exchanging row lists and IPC handles between ranks) stays with the caller - torch.distributed in
-// this repo, MPI in the reference's host code - so this file has no dependency on either.
+// Cross-GPU ordering: epoch-numbered flags in peer memory, release / acquire at system scope:
+//   pushed[j]   (in my flags)  = last epoch for which rank j's rows have landed in my window,
+//   consumed[j] (in my flags)  = last epoch whose window contents rank j has finished reading.
+// The receive window has n_buffers (1 or 2) epoch-alternating buffers: before writing epoch e into peer j's window
+// the pusher waits for consumed[j] >= e - n_buffers.  Every wait is bounded (NTS_EXCHANGE_TIMEOUT_MS, default 30 s):
+// on expiry the kernel records what it was waiting for in a host-mapped word and traps, so a dead or failed peer
+// surfaces as a CUDA error with a message instead of a hang.
+// The CONTROL plane (row lists, IPC handles, barriers) stays with the caller - torch.distributed in this repo, MPI in
+// the reference's host code - so this file depends on neither.
+#include <algorithm>
 #include <vector>
 
 #include "nts_common.cuh"
 
+namespace nts {
+constexpr int kMaxPeers = 32;
+
+struct PushTarget {
+  const uint32_t *rows;          // local row ids to send (nullptr: rows are contiguous from `src_row0`)
+  uint32_t n_rows, src_row0;
+  float *dst;                    // first destination row in the peer's window (peer address)
+  uint32_t *pushed_flag;         // peer address: flags[p] of that peer
+  const uint32_t *consumed_flag; // local address: flags[P + j]
+};
+struct PushArgs {
+  PushTarget t[kMaxPeers];
+  int n;
+  uint32_t epoch, wait_epoch; // wait for consumed >= wait_epoch (0: nothing to wait for)
+};
+} // namespace nts
+
 struct nts_exchange {
+  int P = 1, p = 0;
   nts_exchange_desc d;
-  std::vector<uint32_t> need_count, send_count, recv_offs, peer_bwd_offset;
-  std::vector<const uint32_t *> need;
+  std::vector<nts_exchange_chunk> chunks;
+  std::vector<uint32_t> need_count, send_count, recv_offs, srecv_offs, fwd_push_off, bwd_push_off;
+  uint32_t recv_total = 0, send_total = 0;
+  // exported receive window + flags
   float *window = nullptr;
-  size_t capacity_floats = 0;
-  uint32_t *flags = nullptr;                 // [1 + P]: published, consumed[peer]
-  std::vector<float *> peer_window;          // opened IPC mappings (own entry = window)
+  size_t buf_floats = 0; // floats per epoch buffer
+  int n_buffers = 0;
+  uint32_t *flags = nullptr;          // [2P]: pushed[P], consumed[P]
+  uint32_t *tickets = nullptr;        // [P] CTA arrival counters of the push kernel (local)
+  int *err_host = nullptr, *err_dev = nullptr; // host-mapped diagnostics of a timed-out wait
+  std::vector<float *> peer_window;
   std::vector<uint32_t *> peer_flags;
-  uint32_t **d_peer_flags = nullptr;         // device copy of peer_flags for the signalling kernel
+  uint32_t **d_peer_flags = nullptr;
   bool peers_open = false;
   uint32_t epoch = 0;
-  float *recv = nullptr;                     // receive staging (forward) / pulled slices (backward)
-  size_t recv_cap = 0;
+  float *bsend = nullptr;             // backward partials [recv_total, F] (local)
+  size_t bsend_cap = 0;
   cudaStream_t comm = nullptr;
   cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+  std::vector<cudaEvent_t> ev_peer;   // backward: partial of chunk i finished
+  // preprocessed aggregation per chunk direction (created on first use; nullptr = plain kernel)
+  std::vector<std::vector<std::pair<int, nts_gather_plan *>>> plan_fwd, plan_bwd; // [P] -> (feature width, plan)
+  uint64_t plan_min_edges = 1u << 20;
+  unsigned long long timeout_ns = 30ull * 1000000000ull;
+  int push_ctas = 0;
 };
 
 namespace nts {
 
-__global__ void wait_all_consumed_kernel(const uint32_t *flags, int P, int p, uint32_t value) {
-  const int j = threadIdx.x;
-  if (j >= P || j == p)
-    return;
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
   uint32_t v;
-  do {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + 1 + j) : "memory");
-    if (v < value)
-      __nanosleep(200);
-  } while (v < value);
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= value; on timeout record {code, index, wanted, seen} and trap
+__device__ __forceinline__ void bounded_wait_geq(const uint32_t *flag, uint32_t value, unsigned long long timeout_ns,
+                                                 int *err, int code, int index) {
+  uint32_t v = ld_acquire_sys(flag);
+  if (v >= value)
+    return;
+  const unsigned long long t0 = globaltimer_ns();
+  while ((v = ld_acquire_sys(flag)) < value) {
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > timeout_ns) {
+      if (err) {
+        err[1] = index;
+        err[2] = (int)value;
+        err[3] = (int)v;
+        __threadfence_system();
+        err[0] = code;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
 }
 
+// wait for pushed[i] >= epoch for the listed partitions (one thread each)
+__global__ void wait_pushed_kernel(const uint32_t *flags, uint32_t mask, uint32_t epoch, unsigned long long timeout_ns,
+                                   int *err) {
+  const int i = threadIdx.x;
+  if (i < kMaxPeers && ((mask >> i) & 1u))
+    bounded_wait_geq(flags + i, epoch, timeout_ns, err, 1, i);
+}
+
+// consumed[p] = epoch in every peer's flags
 __global__ void signal_consumed_kernel(uint32_t *const *peer_flags, int P, int p, uint32_t value) {
   const int j = threadIdx.x;
   if (j >= P || j == p)
     return;
   __threadfence_system();
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[j] + 1 + p), "r"(value) : "memory");
+  st_release_sys(peer_flags[j] + P + p, value);
 }
+
+// The persistent push kernel: all CTAs work through the targets in order; a target's flag is raised by the last CTA
+// to finish its share of that target's rows.  VEC floats per lane access (rows are F floats, F % VEC == 0, both
+// sides VEC*4-byte aligned); 4 independent loads in flight per lane.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    push_rows_kernel(const PushArgs a, const float *__restrict__ src, uint32_t F, uint32_t *tickets,
+                     unsigned long long timeout_ns, int *err) {
+  using V = typename Vec<VEC>::type;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint32_t gwarp = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const uint32_t n_warps = gridDim.x * warps_per_cta;
+  const uint32_t nvec = F / VEC;
+  for (int k = 0; k < a.n; k++) {
+    const PushTarget t = a.t[k];
+    if (t.n_rows) {
+      if (a.wait_epoch && threadIdx.x == 0)
+        bounded_wait_geq(t.consumed_flag, a.wait_epoch, timeout_ns, err, 2, k);
+      __syncthreads();
+      for (uint32_t r = gwarp; r < t.n_rows; r += n_warps) {
+        const uint32_t srow = t.rows ? __ldg(t.rows + r) : t.src_row0 + r;
+        const V *s = reinterpret_cast<const V *>(src + (size_t)srow * F);
+        V *d = reinterpret_cast<V *>(t.dst + (size_t)r * F);
+        uint32_t c = lane;
+        for (; c + 96 < nvec; c += 128) {
+          V v0 = __ldg(s + c), v1 = __ldg(s + c + 32), v2 = __ldg(s + c + 64), v3 = __ldg(s + c + 96);
+          d[c] = v0, d[c + 32] = v1, d[c + 64] = v2, d[c + 96] = v3;
+        }
+        for (; c < nvec; c += 32)
+          d[c] = __ldg(s + c);
+      }
+      __threadfence_system(); // my stores to the peer are ordered before the ticket below
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t ticket = atomicAdd(tickets + k, 1u);
+      if (ticket == gridDim.x - 1) { // every CTA has finished this target
+        tickets[k] = 0;
+        __threadfence_system();
+        st_release_sys(t.pushed_flag, a.epoch);
+      }
+    }
+  }
+}
+
+} // namespace nts
+
+using namespace nts;
+
+#define NTS_TRY(expr)                                                                                               \
+  do {                                                                                                              \
+    int nts_rc_ = (expr);                                                                                           \
+    if (nts_rc_ != 0)                                                                                               \
+      return nts_rc_;                                                                                               \
+  } while (0)
 
 static int grow(float **buf, size_t *cap, size_t floats) {
   if (floats <= *cap)
@@ -70,36 +198,146 @@ static int grow(float **buf, size_t *cap, size_t floats) {
   return 0;
 }
 
-} // namespace nts
+// a timed-out wait left a record: turn the launch failure into a message
+static int check_wait_error(nts_exchange *ex, int rc) {
+  if (ex->err_host && ex->err_host[0]) {
+    char msg[256];
+    snprintf(msg, sizeof(msg),
+             "exchange wait timed out on rank %d: %s %d (wanted epoch %d, saw %d) - a peer died, failed or fell out of step",
+             ex->p, ex->err_host[0] == 1 ? "no rows pushed by partition" : "window not consumed by push target",
+             ex->err_host[1], ex->err_host[2], ex->err_host[3]);
+    return fail(rc ? rc : -1, msg, __FILE__, __LINE__);
+  }
+  return rc;
+}
 
-using namespace nts;
+static int launch_push(nts_exchange *ex, const PushArgs &a, const float *src, uint32_t F, cudaStream_t st) {
+  int vec = 1;
+  bool a16 = aligned_to(src, 16), a8 = aligned_to(src, 8);
+  for (int k = 0; k < a.n; k++) {
+    a16 = a16 && aligned_to(a.t[k].dst, 16);
+    a8 = a8 && aligned_to(a.t[k].dst, 8);
+  }
+  if (F % 4 == 0 && a16)
+    vec = 4;
+  else if (F % 2 == 0 && a8)
+    vec = 2;
+  const int ctas = ex->push_ctas;
+  if (vec == 4)
+    push_rows_kernel<4><<<ctas, 256, 0, st>>>(a, src, F, ex->tickets, ex->timeout_ns, ex->err_dev);
+  else if (vec == 2)
+    push_rows_kernel<2><<<ctas, 256, 0, st>>>(a, src, F, ex->tickets, ex->timeout_ns, ex->err_dev);
+  else
+    push_rows_kernel<1><<<ctas, 256, 0, st>>>(a, src, F, ex->tickets, ex->timeout_ns, ex->err_dev);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+// aggregation of one chunk direction: preprocessed plan for big chunks, the plain kernel otherwise
+static int aggregate_chunk(nts_exchange *ex, int i, bool forward, const float *in, float *out, uint32_t F,
+                           cudaStream_t st) {
+  const nts_exchange_chunk &c = ex->chunks[i];
+  const uint32_t n_rows = forward ? ex->d.owned_vertices : ex->need_count[i];
+  const uint32_t gather_rows = forward ? ex->need_count[i] : ex->d.owned_vertices;
+  if (!c.edges || !n_rows)
+    return 0;
+  const nts_vid_t *off = forward ? c.column_offset : c.row_offset_compact;
+  const nts_vid_t *idx = forward ? c.slots : c.column_indices;
+  const float *w = forward ? c.weight_forward : c.weight_backward;
+  const uint32_t base = forward ? 0u : ex->d.dst_start;
+  if (c.edges >= ex->plan_min_edges) {
+    std::vector<std::pair<int, nts_gather_plan *>> &plans = (forward ? ex->plan_fwd : ex->plan_bwd)[i];
+    nts_gather_plan *pl = nullptr;
+    for (auto &e : plans)
+      if (e.first == (int)F)
+        pl = e.second;
+    if (!pl) { // first use of this width: slab count by measurement, built once and kept
+      pl = nts_gather_plan_create_tuned(off, idx, w, nullptr, base, n_rows, c.edges, gather_rows, F, st);
+      if (!pl)
+        return -1;
+      for (auto &e : plans) // another width settled on the same slab count: share its arrays
+        if (nts_gather_plan_slabs(e.second) == nts_gather_plan_slabs(pl)) {
+          nts_gather_plan_destroy(pl);
+          pl = e.second;
+          break;
+        }
+      plans.emplace_back((int)F, pl);
+    }
+    return nts_gather_plan_run(pl, in, out, F, st);
+  }
+  return nts_segment_gather_sum(in, out, w, idx, off, base, n_rows, c.edges, F, st);
+}
 
 extern "C" {
 
 nts_exchange *nts_exchange_create(const nts_exchange_desc *desc) {
-  if (!desc || desc->partitions < 1 || desc->rank < 0 || desc->rank >= desc->partitions) {
-    fail(-1, "bad exchange descriptor", __FILE__, __LINE__);
+  if (!desc || desc->partitions < 1 || desc->partitions > kMaxPeers || desc->rank < 0 ||
+      desc->rank >= desc->partitions) {
+    fail(-1, "bad exchange descriptor (1 <= partitions <= 32)", __FILE__, __LINE__);
     return nullptr;
   }
   nts_exchange *ex = new nts_exchange();
   ex->d = *desc;
-  const int P = desc->partitions;
-  ex->need_count.assign(desc->need_count, desc->need_count + P);
-  ex->send_count.assign(desc->send_count, desc->send_count + P);
-  ex->peer_bwd_offset.assign(desc->peer_bwd_offset, desc->peer_bwd_offset + P);
-  ex->need.assign(desc->need, desc->need + P);
-  ex->recv_offs.assign(P + 1, 0);
-  for (int i = 0; i < P; i++)
-    ex->recv_offs[i + 1] = ex->recv_offs[i] + (i == desc->rank ? 0u : ex->need_count[i]);
+  const int P = ex->P = desc->partitions, p = ex->p = desc->rank;
+  if (P > 1 && !(desc->chunks && desc->need_count && desc->send_count && desc->fwd_push_offset &&
+                 desc->bwd_push_offset)) {
+    fail(-1, "exchange descriptor lacks the per-partition arrays", __FILE__, __LINE__);
+    delete ex;
+    return nullptr;
+  }
+  ex->need_count.assign(P, 0), ex->send_count.assign(P, 0), ex->fwd_push_off.assign(P, 0), ex->bwd_push_off.assign(P, 0);
+  ex->chunks.assign(P, nts_exchange_chunk{});
+  for (int i = 0; i < P && P > 1; i++) {
+    if (i == p)
+      continue;
+    ex->need_count[i] = desc->need_count[i];
+    ex->send_count[i] = desc->send_count[i];
+    ex->fwd_push_off[i] = desc->fwd_push_offset[i];
+    ex->bwd_push_off[i] = desc->bwd_push_offset[i];
+    ex->chunks[i] = desc->chunks[i];
+  }
+  ex->recv_offs.assign(P + 1, 0), ex->srecv_offs.assign(P + 1, 0);
+  for (int i = 0; i < P; i++) {
+    ex->recv_offs[i + 1] = ex->recv_offs[i] + ex->need_count[i];
+    ex->srecv_offs[i + 1] = ex->srecv_offs[i] + ex->send_count[i];
+  }
+  ex->recv_total = ex->recv_offs[P];
+  ex->send_total = ex->srecv_offs[P];
   ex->peer_window.assign(P, nullptr);
   ex->peer_flags.assign(P, nullptr);
-  bool ok = cudaMalloc(reinterpret_cast<void **>(&ex->flags), sizeof(uint32_t) * (1 + P)) == cudaSuccess &&
-            cudaMemset(ex->flags, 0, sizeof(uint32_t) * (1 + P)) == cudaSuccess &&
+  ex->plan_fwd.resize(P), ex->plan_bwd.resize(P);
+  ex->ev_peer.assign(P, nullptr);
+  if (const char *t = getenv("NTS_EXCHANGE_TIMEOUT_MS")) {
+    const long ms = atol(t);
+    if (ms > 0)
+      ex->timeout_ns = (unsigned long long)ms * 1000000ull;
+  }
+  if (const char *t = getenv("NTS_EXCHANGE_PLAN_MIN_EDGES"))
+    ex->plan_min_edges = strtoull(t, nullptr, 10);
+  ex->push_ctas = std::max(8, sm_count() / 3); // enough memory-level parallelism for NVLink, a third of the SMs at most
+  if (const char *t = getenv("NTS_EXCHANGE_PUSH_CTAS")) {
+    const int n = atoi(t);
+    if (n > 0)
+      ex->push_ctas = n;
+  }
+  int lo = 0, hi = 0;
+  bool ok = cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&ex->flags), sizeof(uint32_t) * 2 * P) == cudaSuccess &&
+            cudaMemset(ex->flags, 0, sizeof(uint32_t) * 2 * P) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&ex->tickets), sizeof(uint32_t) * kMaxPeers) == cudaSuccess &&
+            cudaMemset(ex->tickets, 0, sizeof(uint32_t) * kMaxPeers) == cudaSuccess &&
             cudaMalloc(reinterpret_cast<void **>(&ex->d_peer_flags), sizeof(uint32_t *) * P) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&ex->comm, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaHostAlloc(reinterpret_cast<void **>(&ex->err_host), 4 * sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer(reinterpret_cast<void **>(&ex->err_dev), ex->err_host, 0) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&ex->comm, cudaStreamNonBlocking, hi) == cudaSuccess &&
             cudaEventCreateWithFlags(&ex->ev_main, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ex->ev_comm, cudaEventDisableTiming) == cudaSuccess &&
-            cudaDeviceSynchronize() == cudaSuccess;
+            cudaEventCreateWithFlags(&ex->ev_comm, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < P && ok; i++)
+    ok = cudaEventCreateWithFlags(&ex->ev_peer[i], cudaEventDisableTiming) == cudaSuccess;
+  if (ok) {
+    memset(ex->err_host, 0, 4 * sizeof(int));
+    ok = cudaDeviceSynchronize() == cudaSuccess;
+  }
   if (!ok) {
     fail(-1, "exchange resource allocation failed", __FILE__, __LINE__);
     delete ex;
@@ -108,59 +346,85 @@ nts_exchange *nts_exchange_create(const nts_exchange_desc *desc) {
   return ex;
 }
 
-int nts_exchange_destroy(nts_exchange *ex) {
-  if (!ex)
-    return 0;
-  cudaDeviceSynchronize();
-  if (ex->peers_open)
-    for (int j = 0; j < ex->d.partitions; j++)
-      if (j != ex->d.rank) {
-        cudaIpcCloseMemHandle(ex->peer_window[j]);
-        cudaIpcCloseMemHandle(ex->peer_flags[j]);
-      }
-  cudaFree(ex->window);
-  cudaFree(ex->flags);
-  cudaFree(ex->d_peer_flags);
-  cudaFree(ex->recv);
-  cudaStreamDestroy(ex->comm);
-  cudaEventDestroy(ex->ev_main);
-  cudaEventDestroy(ex->ev_comm);
-  delete ex;
-  return 0;
-}
-
-// Rows the window must hold for feature width F: my own rows (forward) or the partials for all peers (backward).
-uint64_t nts_exchange_required_floats(const nts_exchange *ex, nts_vid_t feature_size) {
-  uint64_t rows = ex->d.owned_vertices;
-  if (ex->d.recv_total > rows)
-    rows = ex->d.recv_total;
-  if (rows == 0)
-    rows = 1;
-  return rows * (uint64_t)feature_size;
-}
-
-// (Re)allocate the exported window.  COLLECTIVE in effect: after it returns 1 on any rank, every rank must exchange
-// the new handles and call nts_exchange_open_peers again before the next forward/backward.
-int nts_exchange_reserve(nts_exchange *ex, uint64_t floats, int *reallocated) {
-  NTS_ARG_CHECK(ex && reallocated, "null argument");
-  *reallocated = 0;
-  if (floats <= ex->capacity_floats)
-    return 0;
-  NTS_CUDA_OK(cudaDeviceSynchronize());
+int nts_exchange_release_peers(nts_exchange *ex) {
+  NTS_ARG_CHECK(ex != nullptr, "null engine");
+  NTS_CUDA_OK(cudaDeviceSynchronize()); // my pushes into the peers' windows and my reads of my own are done
   if (ex->peers_open) {
-    for (int j = 0; j < ex->d.partitions; j++)
-      if (j != ex->d.rank) {
+    for (int j = 0; j < ex->P; j++)
+      if (j != ex->p) {
         NTS_CUDA_OK(cudaIpcCloseMemHandle(ex->peer_window[j]));
         NTS_CUDA_OK(cudaIpcCloseMemHandle(ex->peer_flags[j]));
       }
     ex->peers_open = false;
   }
+  return 0;
+}
+
+int nts_exchange_destroy(nts_exchange *ex) {
+  if (!ex)
+    return 0;
+  cudaDeviceSynchronize();
+  if (ex->peers_open)
+    for (int j = 0; j < ex->P; j++)
+      if (j != ex->p) {
+        cudaIpcCloseMemHandle(ex->peer_window[j]);
+        cudaIpcCloseMemHandle(ex->peer_flags[j]);
+      }
+  for (auto *side : {&ex->plan_fwd, &ex->plan_bwd})
+    for (auto &per_chunk : *side) {
+      std::vector<nts_gather_plan *> freed; // widths may share a plan
+      for (auto &e : per_chunk)
+        if (std::find(freed.begin(), freed.end(), e.second) == freed.end()) {
+          nts_gather_plan_destroy(e.second);
+          freed.push_back(e.second);
+        }
+    }
+  cudaFree(ex->window);
+  cudaFree(ex->flags);
+  cudaFree(ex->tickets);
+  cudaFree(ex->d_peer_flags);
+  cudaFree(ex->bsend);
+  if (ex->err_host)
+    cudaFreeHost(ex->err_host);
+  if (ex->comm)
+    cudaStreamDestroy(ex->comm);
+  if (ex->ev_main)
+    cudaEventDestroy(ex->ev_main);
+  if (ex->ev_comm)
+    cudaEventDestroy(ex->ev_comm);
+  for (cudaEvent_t e : ex->ev_peer)
+    if (e)
+      cudaEventDestroy(e);
+  delete ex;
+  return 0;
+}
+
+// Floats ONE epoch buffer of the receive window must hold for feature width F: the rows I read from peers (forward)
+// or the partial gradients peers return for my rows (backward).
+uint64_t nts_exchange_required_floats(const nts_exchange *ex, nts_vid_t feature_size) {
+  uint64_t rows = std::max(ex->recv_total, ex->send_total);
+  if (rows == 0)
+    rows = 1;
+  return rows * (uint64_t)feature_size;
+}
+
+uint64_t nts_exchange_capacity_floats(const nts_exchange *ex) { return ex ? ex->buf_floats : 0; }
+
+// (Re)allocate the exported receive window: n_buffers epoch buffers of floats_per_buffer floats.
+// CONTRACT (collective): a window may only be replaced when no rank still maps it or writes into it.  Sequence on
+// EVERY rank: nts_exchange_release_peers -> barrier (caller's control plane) -> nts_exchange_reserve ->
+// nts_exchange_handles -> (all-gather of the handles) -> nts_exchange_open_peers -> barrier.
+int nts_exchange_reserve(nts_exchange *ex, uint64_t floats_per_buffer, int n_buffers) {
+  NTS_ARG_CHECK(ex && (n_buffers == 1 || n_buffers == 2), "bad argument (n_buffers must be 1 or 2)");
+  NTS_ARG_CHECK(!ex->peers_open, "nts_exchange_release_peers (and a barrier) must precede nts_exchange_reserve");
+  NTS_CUDA_OK(cudaDeviceSynchronize());
   if (ex->window)
     NTS_CUDA_OK(cudaFree(ex->window));
   ex->window = nullptr;
-  NTS_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&ex->window), floats * sizeof(float)));
-  ex->capacity_floats = floats;
-  *reallocated = 1;
+  ex->buf_floats = 0;
+  NTS_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&ex->window), floats_per_buffer * n_buffers * sizeof(float)));
+  ex->buf_floats = floats_per_buffer;
+  ex->n_buffers = n_buffers;
   return 0;
 }
 
@@ -178,7 +442,8 @@ int nts_exchange_handles(nts_exchange *ex, unsigned char window_handle[NTS_IPC_H
 // handles: P consecutive 64-byte window handles and P consecutive flag handles (own entries ignored)
 int nts_exchange_open_peers(nts_exchange *ex, const unsigned char *window_handles, const unsigned char *flag_handles) {
   NTS_ARG_CHECK(ex && window_handles && flag_handles, "null argument");
-  const int P = ex->d.partitions, p = ex->d.rank;
+  NTS_ARG_CHECK(!ex->peers_open, "peers already open");
+  const int P = ex->P, p = ex->p;
   for (int j = 0; j < P; j++) {
     if (j == p) {
       ex->peer_window[j] = ex->window;
@@ -199,118 +464,130 @@ int nts_exchange_open_peers(nts_exchange *ex, const unsigned char *window_handle
   return 0;
 }
 
-static int begin_epoch(nts_exchange *ex, cudaStream_t st, uint32_t *epoch) {
-  ex->epoch += 1;
-  *epoch = ex->epoch;
-  if (ex->epoch > 1 && ex->d.partitions > 1) { // every peer is done reading what I published last time
-    wait_all_consumed_kernel<<<1, 32 * ((ex->d.partitions + 31) / 32), 0, st>>>(ex->flags, ex->d.partitions, ex->d.rank,
-                                                                               ex->epoch - 1);
-    NTS_LAUNCH_CHECK();
-  }
+static int ready_for(nts_exchange *ex, nts_vid_t F) {
+  NTS_ARG_CHECK(ex->peers_open && ex->n_buffers >= 1 && nts_exchange_required_floats(ex, F) <= ex->buf_floats,
+                "exchange window not reserved / peers not opened for this feature width");
   return 0;
 }
 
-static int signal_consumed(nts_exchange *ex, uint32_t epoch, cudaStream_t st) {
-  signal_consumed_kernel<<<1, 32 * ((ex->d.partitions + 31) / 32), 0, st>>>(ex->d_peer_flags, ex->d.partitions,
-                                                                           ex->d.rank, epoch);
-  NTS_LAUNCH_CHECK();
-  return 0;
-}
-
-#define NTS_TRY(expr)                                                                                               \
-  do {                                                                                                              \
-    int nts_rc_ = (expr);                                                                                           \
-    if (nts_rc_ != 0)                                                                                               \
-      return nts_rc_;                                                                                               \
-  } while (0)
-
-// Y_p += sum_i A_{p<-i} X_i.  `y` must be zeroed by the caller (accumulate semantics, like every aggregation entry).
-int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t F, void *stream) {
-  NTS_ARG_CHECK(ex != nullptr, "null engine");
+static int forward_impl(nts_exchange *ex, const float *x, float *y, nts_vid_t F, void *stream) {
   const nts_exchange_desc &d = ex->d;
   // a rank that owns no vertices (the 1024-aligned partitioner leaves such ranks on small graphs) has no rows to
-  // publish or produce, but still takes part in the flag protocol below
+  // push or produce, but still takes part in the flag protocol below
   NTS_ARG_CHECK(d.owned_vertices == 0 || (x && y), "null feature pointer");
   cudaStream_t st = as_stream(stream);
-  const int P = d.partitions, p = d.rank;
+  const int P = ex->P, p = ex->p;
   if (P == 1)
     return nts_gather_by_dst_from_src(x, y, d.local_weight_forward, d.local_row_indices, d.local_column_offset,
                                       d.dst_start, d.dst_start + d.owned_vertices, d.dst_start,
                                       d.dst_start + d.owned_vertices, d.local_edges, d.owned_vertices, F, 1, stream);
-  NTS_ARG_CHECK(ex->peers_open && nts_exchange_required_floats(ex, F) <= ex->capacity_floats,
-                "exchange window not reserved / peers not opened for this feature width");
-  uint32_t epoch = 0;
-  NTS_TRY(begin_epoch(ex, st, &epoch));
-  NTS_CUDA_OK(cudaMemcpyAsync(ex->window, x, (size_t)d.owned_vertices * F * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  NTS_TRY(nts_signal_set(ex->flags, epoch, st));                     // published
-  NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st));
-  NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
-  NTS_TRY(grow(&ex->recv, &ex->recv_cap, (size_t)(d.recv_total ? d.recv_total : 1) * F));
-  for (int s = 1; s < P; s++) {                                      // the reference's ring order (p+1, p+2, ...)
-    const int i = (p + s) % P;
-    const uint32_t n = ex->need_count[i];
-    if (!n)
-      continue;
-    NTS_TRY(nts_signal_wait_geq(ex->peer_flags[i], epoch, ex->comm));
-    NTS_TRY(nts_gather_rows(ex->recv + (size_t)ex->recv_offs[i] * F, ex->peer_window[i], ex->need[i], n, F, ex->comm));
+  NTS_TRY(ready_for(ex, F));
+  const uint32_t epoch = ++ex->epoch;
+  const size_t buf = (size_t)(epoch % ex->n_buffers) * ex->buf_floats;
+  // ---- side stream: push my rows to every peer, ring order p-1, p-2, ... (the peer that needs them first)
+  PushArgs a;
+  a.n = 0;
+  a.epoch = epoch;
+  a.wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
+  for (int s = 1; s < P; s++) {
+    const int j = (p - s + P) % P;
+    PushTarget &t = a.t[a.n++];
+    t.rows = d.send_rows_all + ex->srecv_offs[j];
+    t.n_rows = ex->send_count[j];
+    t.src_row0 = 0;
+    t.dst = ex->peer_window[j] + buf + (size_t)ex->fwd_push_off[j] * F;
+    t.pushed_flag = ex->peer_flags[j] + p;
+    t.consumed_flag = ex->flags + P + j;
   }
-  NTS_TRY(signal_consumed(ex, epoch, ex->comm));
-  NTS_CUDA_OK(cudaEventRecord(ex->ev_comm, ex->comm));
-  // local chunk overlaps with the pulls
+  NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st)); // x is ready
+  NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
+  NTS_TRY(launch_push(ex, a, x, F, ex->comm));
+  // ---- main stream: local chunk, then the remote chunks as their rows arrive
   NTS_TRY(nts_gather_by_dst_from_src(x, y, d.local_weight_forward, d.local_row_indices, d.local_column_offset, d.dst_start,
                                      d.dst_start + d.owned_vertices, d.dst_start, d.dst_start + d.owned_vertices,
                                      d.local_edges, d.owned_vertices, F, 1, st));
+  for (int s = 1; s < P; s++) {
+    const int i = (p + s) % P;
+    wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, 1u << i, epoch, ex->timeout_ns, ex->err_dev);
+    NTS_LAUNCH_CHECK();
+    if (ex->need_count[i])
+      NTS_TRY(aggregate_chunk(ex, i, true, ex->window + buf + (size_t)ex->recv_offs[i] * F, y, F, st));
+  }
+  signal_consumed_kernel<<<1, 32, 0, st>>>(ex->d_peer_flags, P, p, epoch);
+  NTS_LAUNCH_CHECK();
+  // the next call on `st` may overwrite x: it must not start before the push kernel has read it
+  NTS_CUDA_OK(cudaEventRecord(ex->ev_comm, ex->comm));
   NTS_CUDA_OK(cudaStreamWaitEvent(st, ex->ev_comm, 0));
-  if (d.remote_edges)
-    NTS_TRY(nts_segment_gather_sum(ex->recv, y, d.remote_weight, d.remote_slots, d.remote_column_offset, 0,
-                                   d.owned_vertices, d.remote_edges, F, st));
   return 0;
+}
+
+static int backward_impl(nts_exchange *ex, const float *g, float *dx, nts_vid_t F, void *stream) {
+  const nts_exchange_desc &d = ex->d;
+  NTS_ARG_CHECK(d.owned_vertices == 0 || (g && dx), "null gradient pointer");
+  cudaStream_t st = as_stream(stream);
+  const int P = ex->P, p = ex->p;
+  if (P == 1)
+    return nts_gather_by_src_from_dst(g, dx, d.local_weight_backward, d.local_row_offset, d.local_column_indices,
+                                      d.dst_start, d.dst_start + d.owned_vertices, d.dst_start,
+                                      d.dst_start + d.owned_vertices, d.local_edges, d.owned_vertices, F, 1, stream);
+  NTS_TRY(ready_for(ex, F));
+  const uint32_t epoch = ++ex->epoch;
+  const size_t buf = (size_t)(epoch % ex->n_buffers) * ex->buf_floats;
+  const uint32_t wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
+  NTS_TRY(grow(&ex->bsend, &ex->bsend_cap, (size_t)(ex->recv_total ? ex->recv_total : 1) * F));
+  if (ex->recv_total)
+    NTS_CUDA_OK(cudaMemsetAsync(ex->bsend, 0, (size_t)ex->recv_total * F * sizeof(float), st));
+  // ---- per remote chunk (p+1, p+2, ...): partial gradients of its active sources -> pushed to the owner at once
+  for (int s = 1; s < P; s++) {
+    const int i = (p + s) % P;
+    float *slice = ex->bsend + (size_t)ex->recv_offs[i] * F;
+    if (ex->need_count[i])
+      NTS_TRY(aggregate_chunk(ex, i, false, g, slice, F, st));
+    NTS_CUDA_OK(cudaEventRecord(ex->ev_peer[i], st));
+    NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_peer[i], 0));
+    PushArgs a;
+    a.n = 1;
+    a.epoch = epoch;
+    a.wait_epoch = wait_epoch;
+    PushTarget &t = a.t[0];
+    t.rows = nullptr;
+    t.n_rows = ex->need_count[i];
+    t.src_row0 = ex->recv_offs[i];
+    t.dst = ex->peer_window[i] + buf + (size_t)ex->bwd_push_off[i] * F;
+    t.pushed_flag = ex->peer_flags[i] + p;
+    t.consumed_flag = ex->flags + P + i;
+    NTS_TRY(launch_push(ex, a, ex->bsend, F, ex->comm));
+  }
+  // ---- local chunk overlaps with the pushes; then everything the peers computed for my rows
+  NTS_TRY(nts_gather_by_src_from_dst(g, dx, d.local_weight_backward, d.local_row_offset, d.local_column_indices,
+                                     d.dst_start, d.dst_start + d.owned_vertices, d.dst_start,
+                                     d.dst_start + d.owned_vertices, d.local_edges, d.owned_vertices, F, 1, st));
+  uint32_t mask = 0;
+  for (int j = 0; j < P; j++)
+    if (j != p)
+      mask |= 1u << j;
+  wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, mask, epoch, ex->timeout_ns, ex->err_dev);
+  NTS_LAUNCH_CHECK();
+  if (ex->send_total)
+    NTS_TRY(nts_scatter_add_rows_atomic(dx, ex->window + buf, d.send_rows_all, ex->send_total, F, st));
+  signal_consumed_kernel<<<1, 32, 0, st>>>(ex->d_peer_flags, P, p, epoch);
+  NTS_LAUNCH_CHECK();
+  // bsend is rewritten by the next backward on `st`: the pushes must have read it
+  NTS_CUDA_OK(cudaEventRecord(ex->ev_comm, ex->comm));
+  NTS_CUDA_OK(cudaStreamWaitEvent(st, ex->ev_comm, 0));
+  return 0;
+}
+
+// Y_p += sum_i A_{p<-i} X_i.  `y` must be zeroed by the caller (accumulate semantics, like every aggregation entry).
+int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t F, void *stream) {
+  NTS_ARG_CHECK(ex != nullptr, "null engine");
+  return check_wait_error(ex, forward_impl(ex, x, y, F, stream));
 }
 
 // dX_p += sum_j A_{j<-p}^T dY_j.  `dx` must be zeroed by the caller.
 int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t F, void *stream) {
   NTS_ARG_CHECK(ex != nullptr, "null engine");
-  const nts_exchange_desc &d = ex->d;
-  NTS_ARG_CHECK(d.owned_vertices == 0 || (g && dx), "null gradient pointer");
-  cudaStream_t st = as_stream(stream);
-  const int P = d.partitions, p = d.rank;
-  if (P == 1)
-    return nts_gather_by_src_from_dst(g, dx, d.local_weight_backward, d.local_row_offset, d.local_column_indices,
-                                      d.dst_start, d.dst_start + d.owned_vertices, d.dst_start,
-                                      d.dst_start + d.owned_vertices, d.local_edges, d.owned_vertices, F, 1, stream);
-  NTS_ARG_CHECK(ex->peers_open && nts_exchange_required_floats(ex, F) <= ex->capacity_floats,
-                "exchange window not reserved / peers not opened for this feature width");
-  uint32_t epoch = 0;
-  NTS_TRY(begin_epoch(ex, st, &epoch));
-  if (d.recv_total) {
-    NTS_CUDA_OK(cudaMemsetAsync(ex->window, 0, (size_t)d.recv_total * F * sizeof(float), st));
-    if (d.remote_edges)
-      NTS_TRY(nts_segment_gather_sum(g, ex->window, d.backward_weight, d.backward_indices, d.backward_offsets,
-                                     d.dst_start, d.recv_total, d.remote_edges, F, st));
-  }
-  NTS_TRY(nts_signal_set(ex->flags, epoch, st));                     // published
-  NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st));
-  NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
-  NTS_TRY(grow(&ex->recv, &ex->recv_cap, (size_t)(d.send_total ? d.send_total : 1) * F));
-  size_t pos = 0;
-  for (int j = 0; j < P; j++) {                                      // staging order = order of send_rows_all
-    const uint32_t n = ex->send_count[j];
-    if (j == p || !n)
-      continue;
-    NTS_TRY(nts_signal_wait_geq(ex->peer_flags[j], epoch, ex->comm));
-    NTS_CUDA_OK(cudaMemcpyAsync(ex->recv + pos * F, ex->peer_window[j] + (size_t)ex->peer_bwd_offset[j] * F,
-                                (size_t)n * F * sizeof(float), cudaMemcpyDeviceToDevice, ex->comm));
-    pos += n;
-  }
-  NTS_TRY(signal_consumed(ex, epoch, ex->comm));
-  NTS_CUDA_OK(cudaEventRecord(ex->ev_comm, ex->comm));
-  NTS_TRY(nts_gather_by_src_from_dst(g, dx, d.local_weight_backward, d.local_row_offset, d.local_column_indices,
-                                     d.dst_start, d.dst_start + d.owned_vertices, d.dst_start,
-                                     d.dst_start + d.owned_vertices, d.local_edges, d.owned_vertices, F, 1, st));
-  NTS_CUDA_OK(cudaStreamWaitEvent(st, ex->ev_comm, 0));
-  if (d.send_total)
-    NTS_TRY(nts_scatter_add_rows_atomic(dx, ex->recv, d.send_rows_all, d.send_total, F, st));
-  return 0;
+  return check_wait_error(ex, backward_impl(ex, g, dx, F, stream));
 }
 
 } // extern "C"

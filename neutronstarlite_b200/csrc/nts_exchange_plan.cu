@@ -21,7 +21,10 @@ struct nts_exchange_plan {
   std::vector<char> have_peer;
   bool finalized = false;
   // merged arrays (host)
-  std::vector<uint32_t> need_count, send_count, peer_bwd_offset, recv_offs;
+  std::vector<uint32_t> need_count, send_count, peer_bwd_offset, bwd_push_offset, recv_offs;
+  // per remote chunk: row_indices as ranks in the need list, row_offset restricted to the active sources
+  std::vector<std::vector<uint32_t>> chunk_slots, chunk_offc;
+  std::vector<nts_exchange_chunk> dev_chunks;
   std::vector<uint32_t> remote_col_offset, remote_slots, bwd_offsets, bwd_indices, send_rows_all;
   std::vector<float> remote_w, bwd_w;
   uint64_t remote_edges = 0;
@@ -166,6 +169,7 @@ int nts_exchange_plan_finalize(nts_exchange_plan *pl) {
   pl->need_count.assign(P, 0);
   pl->send_count.assign(P, 0);
   pl->peer_bwd_offset.assign(P, 0);
+  pl->bwd_push_offset.assign(P, 0);
   pl->recv_offs.assign(P + 1, 0);
   for (int i = 0; i < P; i++) {
     pl->need_count[i] = i == p ? 0u : (uint32_t)pl->need[i].size();
@@ -175,6 +179,31 @@ int nts_exchange_plan_finalize(nts_exchange_plan *pl) {
     for (int q = 0; q < p; q++)
       before += pl->peer_need_count[i][q];
     pl->peer_bwd_offset[i] = before;
+    uint32_t grads_before = 0; // partial-gradient rows the ranks before me return to rank i = start of mine in its staging
+    for (int q = 0; q < p; q++)
+      if (q != i)
+        grads_before += pl->peer_need_count[q][i];
+    pl->bwd_push_offset[i] = grads_before;
+  }
+  // ---- per remote chunk: slots (rank of the source in the need list) and compact row offsets
+  pl->chunk_slots.assign(P, {});
+  pl->chunk_offc.assign(P, {});
+  for (int i = 0; i < P; i++) {
+    if (i == p)
+      continue;
+    const nts_host_chunk &c = pl->chunks[i];
+    const std::vector<uint32_t> &need = pl->need[i];
+    std::vector<uint32_t> rank_of(c.src_end - c.src_start, 0u);
+    for (size_t k = 0; k < need.size(); k++)
+      rank_of[need[k]] = (uint32_t)k;
+    pl->chunk_slots[i].resize(c.edges);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < (int64_t)c.edges; e++)
+      pl->chunk_slots[i][e] = rank_of[c.row_indices[e] - c.src_start];
+    pl->chunk_offc[i].resize(need.size() + 1);
+    for (size_t k = 0; k < need.size(); k++)
+      pl->chunk_offc[i][k] = c.row_offset[need[k]];
+    pl->chunk_offc[i][need.size()] = (uint32_t)c.edges;
   }
   pl->recv_total = pl->recv_offs[P];
   pl->send_total = 0;
@@ -264,6 +293,8 @@ int nts_exchange_plan_get_view(const nts_exchange_plan *pl, nts_exchange_plan_vi
   v->need_count = pl->need_count.data();
   v->send_count = pl->send_count.data();
   v->peer_bwd_offset = pl->peer_bwd_offset.data();
+  v->fwd_push_offset = pl->peer_bwd_offset.data(); // same number: where partition `rank` starts in rank j's staging
+  v->bwd_push_offset = pl->bwd_push_offset.data();
   v->remote_column_offset = pl->remote_col_offset.empty() ? nullptr : pl->remote_col_offset.data();
   v->remote_slots = pl->remote_slots.empty() ? nullptr : pl->remote_slots.data();
   v->remote_weight = pl->remote_w.empty() ? nullptr : pl->remote_w.data();
@@ -275,12 +306,20 @@ int nts_exchange_plan_get_view(const nts_exchange_plan *pl, nts_exchange_plan_vi
   return 0;
 }
 
-nts_exchange *nts_exchange_create_from_plan(nts_exchange_plan *pl, const nts_vid_t *local_column_offset,
-                                            const nts_vid_t *local_row_indices, const float *local_weight_forward,
-                                            const nts_vid_t *local_row_offset, const nts_vid_t *local_column_indices,
-                                            const float *local_weight_backward) {
-  if (!pl || !pl->finalized) {
-    fail(-1, "nts_exchange_create_from_plan needs a finalized plan", __FILE__, __LINE__);
+int nts_exchange_plan_chunk(const nts_exchange_plan *pl, int i, const nts_vid_t **slots,
+                            const nts_vid_t **row_offset_compact) {
+  NTS_ARG_CHECK(pl && pl->finalized && i >= 0 && i < pl->P && i != pl->p, "bad argument");
+  if (slots)
+    *slots = pl->chunk_slots[i].empty() ? nullptr : pl->chunk_slots[i].data();
+  if (row_offset_compact)
+    *row_offset_compact = pl->chunk_offc[i].data();
+  return 0;
+}
+
+nts_exchange *nts_exchange_create_from_plan(nts_exchange_plan *pl, const nts_device_chunk *device_chunks) {
+  if (!pl || !pl->finalized || !device_chunks) {
+    fail(-1, "nts_exchange_create_from_plan needs a finalized plan and the device arrays of every chunk", __FILE__,
+         __LINE__);
     return nullptr;
   }
   const int P = pl->P, p = pl->p;
@@ -289,39 +328,46 @@ nts_exchange *nts_exchange_create_from_plan(nts_exchange_plan *pl, const nts_vid
   d.rank = p;
   d.owned_vertices = pl->chunks[p].dst_end - pl->chunks[p].dst_start;
   d.dst_start = pl->chunks[p].dst_start;
-  d.local_column_offset = local_column_offset;
-  d.local_row_indices = local_row_indices;
-  d.local_row_offset = local_row_offset;
-  d.local_column_indices = local_column_indices;
-  d.local_weight_forward = local_weight_forward;
-  d.local_weight_backward = local_weight_backward;
+  const nts_device_chunk &mine = device_chunks[p];
+  d.local_column_offset = mine.column_offset;
+  d.local_row_indices = mine.row_indices;
+  d.local_row_offset = mine.row_offset;
+  d.local_column_indices = mine.column_indices;
+  d.local_weight_forward = mine.edge_weight_forward;
+  d.local_weight_backward = mine.edge_weight_backward;
   d.local_edges = (nts_vid_t)pl->chunks[p].edges;
-  if (d.local_edges && !(local_column_offset && local_row_indices && local_row_offset && local_column_indices &&
-                         local_weight_forward && local_weight_backward)) {
+  if (d.local_edges && !(mine.column_offset && mine.row_indices && mine.row_offset && mine.column_indices &&
+                         mine.edge_weight_forward && mine.edge_weight_backward)) {
     fail(-1, "device arrays of the local chunk are missing", __FILE__, __LINE__);
     return nullptr;
   }
-  pl->need_dev.assign(P, nullptr);
+  pl->dev_chunks.assign(P, nts_exchange_chunk{});
   int rc = 0;
-  rc |= upload(pl, pl->remote_col_offset, &d.remote_column_offset);
-  rc |= upload(pl, pl->remote_slots, &d.remote_slots);
-  rc |= upload(pl, pl->remote_w, &d.remote_weight);
-  rc |= upload(pl, pl->bwd_offsets, &d.backward_offsets);
-  rc |= upload(pl, pl->bwd_indices, &d.backward_indices);
-  rc |= upload(pl, pl->bwd_w, &d.backward_weight);
   rc |= upload(pl, pl->send_rows_all, &d.send_rows_all);
-  for (int i = 0; i < P && !rc; i++)
-    if (i != p)
-      rc |= upload(pl, pl->need[i], &pl->need_dev[i]);
+  for (int i = 0; i < P && !rc; i++) {
+    if (i == p)
+      continue;
+    nts_exchange_chunk &c = pl->dev_chunks[i];
+    c.edges = pl->chunks[i].edges;
+    if (c.edges && !(device_chunks[i].column_offset && device_chunks[i].column_indices &&
+                     device_chunks[i].edge_weight_forward && device_chunks[i].edge_weight_backward)) {
+      fail(-1, "device arrays of a remote chunk are missing", __FILE__, __LINE__);
+      return nullptr;
+    }
+    c.column_offset = device_chunks[i].column_offset;
+    c.column_indices = device_chunks[i].column_indices;
+    c.weight_forward = device_chunks[i].edge_weight_forward;
+    c.weight_backward = device_chunks[i].edge_weight_backward;
+    rc |= upload(pl, pl->chunk_slots[i], &c.slots);
+    rc |= upload(pl, pl->chunk_offc[i], &c.row_offset_compact);
+  }
   if (rc)
     return nullptr;
-  d.remote_edges = pl->remote_edges;
-  d.recv_total = pl->recv_total;
-  d.send_total = pl->send_total;
+  d.chunks = pl->dev_chunks.data();
   d.need_count = pl->need_count.data();
-  d.need = pl->need_dev.data();
   d.send_count = pl->send_count.data();
-  d.peer_bwd_offset = pl->peer_bwd_offset.data();
+  d.fwd_push_offset = pl->peer_bwd_offset.data();
+  d.bwd_push_offset = pl->bwd_push_offset.data();
   return nts_exchange_create(&d);
 }
 

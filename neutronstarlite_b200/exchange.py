@@ -16,12 +16,14 @@ What moves, and when (rank p of P, partition i -> chunk i = edges src in part i 
             (replaces aggregate_data_buffer_debug's per-element atomics, cuda/ntsCUDATransferKernel.cuh:49-68).
 
 Transports:
-  "nccl"  one all-to-all(v) of the packed rows (torch.distributed / NCCL over NVLink), on a side stream.
-  "p2p"   no packing and no NCCL on the data path: every rank exports its [V_p, F] buffer through CUDA IPC and the
-          RECEIVER pulls the rows it needs straight out of the peer's HBM over NVLink with `nts_gather_rows` on
-          mapped peer pointers; completion is stream-ordered locally, cross-rank ordering uses system-scope flags
-          (`nts_signal_set` / `nts_signal_wait_geq`).  The pulls overlap the local chunk's aggregation; all remote
-          chunks are then aggregated by ONE launch over a merged CSC (launch-bound regime at 8 GPUs).
+  "nccl"  one all-to-all(v) of the packed rows (torch.distributed / NCCL over NVLink) on a side stream, then ONE
+          launch over the merged CSC of all remote chunks - the baseline.
+  "p2p"   the peer-memory engine (csrc/nts_exchange.cu), no packing and no NCCL on the data path: the OWNER of a row
+          stores it straight into the reader's CUDA-IPC receive window over NVLink (one persistent push kernel per
+          call, ring order), raises an epoch flag (`st.release.sys`), and the reader aggregates chunk (p+s) as soon
+          as the rows of partition (p+s) have landed - the reference's per-chunk pipeline (core/graph.hpp:3678-3719)
+          with the host staging removed.  Backward: per-chunk partials pushed to the owner while the next chunk
+          computes.  Big chunks run through nts_gather_plan (slab count measured per width).
 """
 from __future__ import annotations
 
@@ -149,6 +151,20 @@ class ExchangePlan:
             return g
         return torch.from_numpy(getattr(c, name).view(np.int32))
 
+    def push_offsets(self):
+        """(fwd_push_offset[P], bwd_push_offset[P]) of nts_exchange_desc: where MY rows start inside rank j's receive
+        staging (rows it reads from the partitions before mine) and where MY partial gradients start inside rank i's
+        gradient staging (rows the ranks before me return to i).  Needs every rank's need counts."""
+        P, p = self.P, self.p
+        if P == 1:
+            return [0], [0]
+        mine = [self.need_count[i] if i != p else 0 for i in range(P)]
+        allc = [None] * P
+        dist.all_gather_object(allc, mine, group=self.group)
+        fwd = [int(sum(allc[j][i] for i in range(p) if i != j)) if j != p else 0 for j in range(P)]
+        bwd = [int(sum(allc[j][i] for j in range(p) if j != i)) if i != p else 0 for i in range(P)]
+        return fwd, bwd
+
     def ring(self):
         """Remote chunks in the reference's processing order: (p+1), (p+2), ... mod P."""
         return [(self.p + s) % self.P for s in range(1, self.P)]
@@ -173,6 +189,13 @@ class GpuExchange:
             self._p2p = _PeerWindows(self)
         elif transport not in ("nccl", "p2p"):
             raise ValueError("transport must be 'nccl' or 'p2p'")
+
+    def close(self):
+        """Release the engine (its IPC mappings of the peers' windows) - collective in effect: call it on every rank
+        before the process group goes away."""
+        if self._p2p is not None:
+            self._p2p.close()
+            self._p2p = None
 
     # ---- buffers ---------------------------------------------------------------------------------------------
     def _buf(self, key, rows, F):
@@ -352,24 +375,30 @@ class _PeerWindows:
     between ranks with torch.distributed; the data plane (windows, flags, streams, launch sequence) is
     `nts_exchange_*` in csrc/nts_exchange.cu."""
 
-    def __init__(self, ex):
+    def __init__(self, ex, n_buffers=2):
         import ctypes as C
         self.ex = ex
         P, p = ex.P, ex.p
         pg, plan = ex.pg, ex.plan
         L = _lib.load()
-        # backward: where my slice starts inside peer j's window = rows peer j computes for partitions before me
-        allc = [None] * P
-        dist.all_gather_object(allc, [plan.need_count[i] if i != p else 0 for i in range(P)], group=ex.group)
-        bwd_off = [int(sum(allc[j][:p])) for j in range(P)]
+        self.n_buffers = int(n_buffers)
+        fwd_off, bwd_off = plan.push_offsets()
         c = pg.graph_chunks[p]
         u32 = C.c_uint32 * P
+        chunks = (_lib.ExchangeChunk * P)()
+        for i in range(P):
+            if i == p:
+                continue
+            ci = pg.graph_chunks[i]
+            h = chunks[i]
+            h.column_offset, h.slots = _ptr(ci.column_offset_gpu), _ptr(plan.csc_slots[i])
+            h.weight_forward, h.weight_backward = _ptr(ci.edge_weight_forward_gpu), _ptr(ci.edge_weight_backward_gpu)
+            h.row_offset_compact, h.column_indices = _ptr(plan.csr_offsets_compact[i]), _ptr(ci.column_indices_gpu)
+            h.edges = int(ci.edge_size)
         self._keep = {
             "need_count": u32(*[plan.need_count[i] if i != p else 0 for i in range(P)]),
             "send_count": u32(*[plan.send_count[j] if j != p else 0 for j in range(P)]),
-            "bwd_off": u32(*bwd_off),
-            "need": (C.c_void_p * P)(*[_ptr(plan.need[i]) if plan.need[i] is not None and plan.need[i].numel() else None
-                                       for i in range(P)]),
+            "fwd_off": u32(*fwd_off), "bwd_off": u32(*bwd_off), "chunks": chunks,
         }
         d = _lib.ExchangeDesc()
         d.partitions, d.rank = P, p
@@ -378,61 +407,64 @@ class _PeerWindows:
         d.local_row_offset, d.local_column_indices = _ptr(c.row_offset_gpu), _ptr(c.column_indices_gpu)
         d.local_weight_forward, d.local_weight_backward = _ptr(c.edge_weight_forward_gpu), _ptr(c.edge_weight_backward_gpu)
         d.local_edges = c.edge_size
-        d.remote_column_offset, d.remote_slots = _ptr(plan.remote_col_offset), _ptr(plan.remote_slots)
-        d.remote_weight, d.remote_edges = _ptr(plan.remote_w), plan.remote_edges
-        d.backward_offsets, d.backward_indices = _ptr(plan.bwd_offsets), _ptr(plan.bwd_indices)
-        d.backward_weight = _ptr(plan.bwd_w)
-        d.recv_total, d.send_total = plan.recv_total, plan.send_total
+        d.chunks = chunks
         d.need_count = self._keep["need_count"]
-        d.need = C.cast(self._keep["need"], C.POINTER(C.c_void_p))
         d.send_count = self._keep["send_count"]
         d.send_rows_all = _ptr(plan.send_rows_all)
-        d.peer_bwd_offset = self._keep["bwd_off"]
+        d.fwd_push_offset = self._keep["fwd_off"]
+        d.bwd_push_offset = self._keep["bwd_off"]
         self.handle = L.nts_exchange_create(C.byref(d))
         if not self.handle:
             raise _lib.NtsError("nts_exchange_create failed: " + L.nts_last_error().decode())
-        self._reserved = set()
+
+    def _cpu_collective(self):
+        return dist.get_backend(self.ex.group) != "nccl"
 
     def reserve(self, F):
-        """Make the exported window large enough for feature width F on EVERY rank (collective on first use of a
-        width), exchange the IPC handles and (re)open the peers' windows."""
+        """Make the exported receive window large enough for feature width F on EVERY rank.  Collective whenever a
+        rank needs more than it has (all ranks always hold the same capacity: it is the max over ranks):
+        release peers -> barrier -> reallocate -> all-gather of the IPC handles -> open -> barrier
+        (the contract of nts_exchange_reserve, include/nts_b200.h)."""
         import ctypes as C
-        if F in self._reserved:
-            return
         L = _lib.load()
         ex = self.ex
-        need = torch.tensor([L.nts_exchange_required_floats(self.handle, F)], dtype=torch.int64, device=ex.device)
+        if L.nts_exchange_required_floats(self.handle, F) <= L.nts_exchange_capacity_floats(self.handle) and \
+                F <= getattr(self, "_max_F", 0):
+            return
+        cdev = torch.device("cpu") if self._cpu_collective() else ex.device
+        need = torch.tensor([L.nts_exchange_required_floats(self.handle, F)], dtype=torch.int64, device=cdev)
         dist.all_reduce(need, op=dist.ReduceOp.MAX, group=ex.group)
-        realloc = C.c_int(0)
-        _lib.call("nts_exchange_reserve", self.handle, int(need.item()), C.byref(realloc))
-        flag = torch.tensor([realloc.value], dtype=torch.int64, device=ex.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=ex.group)
-        if flag.item():
-            wh, fh = C.create_string_buffer(64), C.create_string_buffer(64)
-            _lib.call("nts_exchange_handles", self.handle, wh, fh)
-            handles = [None] * ex.P
-            dist.all_gather_object(handles, (bytes(wh.raw), bytes(fh.raw)), group=ex.group)
-            _lib.call("nts_exchange_open_peers", self.handle, b"".join(h[0] for h in handles),
-                      b"".join(h[1] for h in handles))
-            dist.barrier(group=ex.group)
-        self._reserved.add(F)
+        self._max_F = max(F, getattr(self, "_max_F", 0))
+        if int(need.item()) <= L.nts_exchange_capacity_floats(self.handle):
+            return
+        _lib.call("nts_exchange_release_peers", self.handle)
+        dist.barrier(group=ex.group)
+        _lib.call("nts_exchange_reserve", self.handle, int(need.item()), self.n_buffers)
+        wh, fh = C.create_string_buffer(64), C.create_string_buffer(64)
+        _lib.call("nts_exchange_handles", self.handle, wh, fh)
+        handles = [None] * ex.P
+        dist.all_gather_object(handles, (bytes(wh.raw), bytes(fh.raw)), group=ex.group)
+        _lib.call("nts_exchange_open_peers", self.handle, b"".join(h[0] for h in handles),
+                  b"".join(h[1] for h in handles))
+        dist.barrier(group=ex.group)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.load().nts_exchange_destroy(self.handle)
+            self.handle = None
 
     def __del__(self):
         try:
-            if getattr(self, "handle", None):
-                _lib.load().nts_exchange_destroy(self.handle)
-                self.handle = None
+            self.close()
         except Exception:
             pass
 
 
-_default = {}
-
-
 def default_exchange(pg):
-    """One exchange object per PartitionedGraph (created lazily by ForwardGPUfuseOp)."""
-    ex = _default.get(id(pg))
+    """One exchange object per PartitionedGraph (created lazily by ForwardGPUfuseOp), kept ON the graph object so
+    that it dies with it (an id()-keyed cache would hand a recycled id a stale plan)."""
+    ex = pg.__dict__.get("_default_exchange")
     if ex is None:
         ex = GpuExchange(pg, transport="nccl")
-        _default[id(pg)] = ex
+        pg.__dict__["_default_exchange"] = ex
     return ex

@@ -72,15 +72,102 @@ def segment_gather_sum(out, x, weight, indices, offsets, index_base, n_rows, n_e
     return out
 
 
+class GatherPlan:
+    """nts_gather_plan (include/nts_b200.h): one chunk direction preprocessed once for repeated aggregation -
+    source-slab bucketing (L2 residency), interleaved (row, weight) pairs, 16-byte aligned gathers."""
+
+    def __init__(self, offsets, indices, weight, index_base, n_rows, n_edges, gather_rows, slabs, slot_of=None,
+                 tune_for=0):
+        """slabs > 0: that many source slabs; slabs == 0: the slab count is MEASURED for feature width `tune_for`
+        (nts_gather_plan_create_tuned)."""
+        L = _lib.load()
+        if slabs > 0:
+            self.handle = L.nts_gather_plan_create(_ptr(offsets), _ptr(indices), _ptr(weight), _ptr(slot_of),
+                                                   int(index_base), int(n_rows), int(n_edges), int(gather_rows),
+                                                   int(slabs), _stream())
+        else:
+            self.handle = L.nts_gather_plan_create_tuned(_ptr(offsets), _ptr(indices), _ptr(weight), _ptr(slot_of),
+                                                         int(index_base), int(n_rows), int(n_edges),
+                                                         int(gather_rows), int(tune_for), _stream())
+        if not self.handle:
+            raise _lib.NtsError("nts_gather_plan_create failed: " + L.nts_last_error().decode(errors="replace"))
+        self.slabs = int(L.nts_gather_plan_slabs(self.handle))
+        self.n_rows, self.n_edges = int(n_rows), int(n_edges)
+
+    def run(self, x, out):
+        _lib.call("nts_gather_plan_run", self.handle, _ptr(x), _ptr(out), int(x.shape[1]), _stream())
+        return out
+
+    def bytes(self):
+        return int(_lib.load().nts_gather_plan_bytes(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().nts_gather_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+# Plan policy: "auto" preprocesses chunks with at least PLAN_MIN_EDGES edges on first use (the arrays of a chunk are
+# immutable, like the reference's CopyGraphToDevice uploads); "off" always takes the plain kernel on the reference
+# layout; "on" plans every chunk.  NTS_PLAN / NTS_PLAN_SLABS are measurement overrides.
+import os as _os
+
+PLAN_MIN_EDGES = 1 << 20
+_plan_mode = {"0": "off", "1": "on"}.get(_os.environ.get("NTS_PLAN", ""), "auto")
+_plan_slabs = int(_os.environ.get("NTS_PLAN_SLABS", "0"))
+
+
+def set_plan_mode(mode, slabs=0):
+    """mode in {"auto", "on", "off"}; slabs > 0 forces the slab count (0 = nts_gather_plan_pick_slabs)."""
+    global _plan_mode, _plan_slabs
+    if mode not in ("auto", "on", "off"):
+        raise ValueError("plan mode must be auto, on or off")
+    _plan_mode, _plan_slabs = mode, int(slabs)
+
+
+def _chunk_plan(chunk, direction, F):
+    """The GatherPlan of one chunk direction for feature width F, or None when the plain kernel should run."""
+    if _plan_mode == "off" or (_plan_mode == "auto" and chunk.edge_size < PLAN_MIN_EDGES):
+        return None
+    if direction == "fwd":
+        n_rows, gather_rows = chunk.batch_size_forward, chunk.batch_size_backward
+    else:
+        n_rows, gather_rows = chunk.batch_size_backward, chunk.batch_size_forward
+    plans = chunk.__dict__.setdefault("_gather_plans", {})      # (direction, slabs) -> plan
+    tuned = chunk.__dict__.setdefault("_gather_plan_for", {})   # (direction, F) -> plan picked by measurement
+    key = (direction, _plan_slabs) if _plan_slabs else (direction, "F", int(F))
+    plan = plans.get(key) if _plan_slabs else tuned.get(key)
+    if plan is None:
+        if direction == "fwd":
+            plan = GatherPlan(chunk.column_offset_gpu, chunk.row_indices_gpu, chunk.edge_weight_forward_gpu,
+                              chunk.src_range[0], n_rows, chunk.edge_size, gather_rows, _plan_slabs, tune_for=int(F))
+        else:
+            plan = GatherPlan(chunk.row_offset_gpu, chunk.column_indices_gpu, chunk.edge_weight_backward_gpu,
+                              chunk.dst_range[0], n_rows, chunk.edge_size, gather_rows, _plan_slabs, tune_for=int(F))
+        if (direction, plan.slabs) in plans:     # another width already settled on this slab count: share the arrays
+            plan = plans[(direction, plan.slabs)]
+        plans[(direction, plan.slabs)] = plan
+        if not _plan_slabs:
+            tuned[key] = plan
+    return plan
+
+
 def gather_by_dst_from_src(chunk, out, x, with_weight=True):
     """NtsScheduler::GatherByDstFromSrc (core/NtsScheduler.hpp:151-191) on one chunk."""
+    plan = _chunk_plan(chunk, "fwd", x.shape[1]) if with_weight else None
     ev = _timer.bracket("fwd", x.shape[1], chunk.edge_size, chunk.batch_size_forward) if _timer else None
     if ev:
         ev[0].record()
-    _lib.call("nts_gather_by_dst_from_src", _ptr(x), _ptr(out), _ptr(chunk.edge_weight_forward_gpu),
-              _ptr(chunk.row_indices_gpu), _ptr(chunk.column_offset_gpu), chunk.src_range[0], chunk.src_range[1],
-              chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_forward,
-              int(x.shape[1]), 1 if with_weight else 0, _stream())
+    if plan is not None:
+        plan.run(x, out)
+    else:
+        _lib.call("nts_gather_by_dst_from_src", _ptr(x), _ptr(out), _ptr(chunk.edge_weight_forward_gpu),
+                  _ptr(chunk.row_indices_gpu), _ptr(chunk.column_offset_gpu), chunk.src_range[0], chunk.src_range[1],
+                  chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_forward,
+                  int(x.shape[1]), 1 if with_weight else 0, _stream())
     if ev:
         ev[1].record()
     return out
@@ -88,13 +175,17 @@ def gather_by_dst_from_src(chunk, out, x, with_weight=True):
 
 def gather_by_src_from_dst(chunk, out, grad, with_weight=True):
     """NtsScheduler::GatherBySrcFromDst (core/NtsScheduler.hpp:257-293) on one chunk."""
+    plan = _chunk_plan(chunk, "bwd", grad.shape[1]) if with_weight else None
     ev = _timer.bracket("bwd", grad.shape[1], chunk.edge_size, chunk.batch_size_backward) if _timer else None
     if ev:
         ev[0].record()
-    _lib.call("nts_gather_by_src_from_dst", _ptr(grad), _ptr(out), _ptr(chunk.edge_weight_backward_gpu),
-              _ptr(chunk.row_offset_gpu), _ptr(chunk.column_indices_gpu), chunk.src_range[0], chunk.src_range[1],
-              chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_backward,
-              int(grad.shape[1]), 1 if with_weight else 0, _stream())
+    if plan is not None:
+        plan.run(grad, out)
+    else:
+        _lib.call("nts_gather_by_src_from_dst", _ptr(grad), _ptr(out), _ptr(chunk.edge_weight_backward_gpu),
+                  _ptr(chunk.row_offset_gpu), _ptr(chunk.column_indices_gpu), chunk.src_range[0], chunk.src_range[1],
+                  chunk.dst_range[0], chunk.dst_range[1], chunk.edge_size, chunk.batch_size_backward,
+                  int(grad.shape[1]), 1 if with_weight else 0, _stream())
     if ev:
         ev[1].record()
     return out

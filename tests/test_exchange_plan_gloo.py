@@ -90,6 +90,19 @@ def _check_cxx_plan(pg, plan, rank, P):
         allc = [None] * P
         dist.all_gather_object(allc, [plan.need_count[i] if i != rank else 0 for i in range(P)])
         assert list(arr_of(v.peer_bwd_offset, P, np.uint32)) == [int(sum(allc[j][:rank])) for j in range(P)]
+        # push offsets as exchange.py::ExchangePlan.push_offsets derives them (own entries are unused)
+        fwd, bwd = plan.push_offsets()
+        assert [int(x) if j != rank else 0 for j, x in enumerate(arr_of(v.fwd_push_offset, P, np.uint32))] == fwd
+        assert [int(x) if j != rank else 0 for j, x in enumerate(arr_of(v.bwd_push_offset, P, np.uint32))] == bwd
+        # per-chunk arrays of the engine == the Python plan's
+        for i in range(P):
+            if i == rank:
+                continue
+            sl, oc = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+            assert L.nts_exchange_plan_chunk(cp, i, C.byref(sl), C.byref(oc)) == 0
+            Ei = int(pg.graph_chunks[i].edge_size)
+            assert np.array_equal(arr_of(sl, Ei, np.uint32), u32(plan.csc_slots[i]))
+            assert np.array_equal(arr_of(oc, plan.need_count[i] + 1, np.uint32), u32(plan.csr_offsets_compact[i]))
     finally:
         L.nts_exchange_plan_destroy(cp)
 

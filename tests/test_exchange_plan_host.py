@@ -84,6 +84,8 @@ class _Rank:
                "remote_edges": int(v.remote_edges),
                "need_count": _np(v.need_count, P, np.uint32), "send_count": _np(v.send_count, P, np.uint32),
                "peer_bwd_offset": _np(v.peer_bwd_offset, P, np.uint32),
+               "fwd_push_offset": _np(v.fwd_push_offset, P, np.uint32),
+               "bwd_push_offset": _np(v.bwd_push_offset, P, np.uint32),
                "remote_column_offset": _np(v.remote_column_offset, v.owned_vertices + 1 if v.remote_edges else 0, np.uint32),
                "remote_slots": _np(v.remote_slots, int(v.remote_edges), np.uint32),
                "remote_weight": _np(v.remote_weight, int(v.remote_edges), np.float32),
@@ -174,6 +176,100 @@ def test_plan_replays_the_reference_exchange(golden):
                 pos += n
             ref = g.mat(r, "gcn_dX")
             _close(dx, ref)
+    finally:
+        for a in ranks:
+            a.close()
+
+
+def _plan_chunk(plan, i, edges, need_n):
+    sl, oc = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+    assert _lib.load().nts_exchange_plan_chunk(plan, i, C.byref(sl), C.byref(oc)) == 0
+    return _np(sl, edges, np.uint32), _np(oc, need_n + 1, np.uint32)
+
+
+def test_plan_replays_the_push_engine(golden):
+    """The data path of csrc/nts_exchange.cu (PUSH model, one stage per source partition) walked in numpy on the C++
+    plan's per-chunk arrays and push offsets: every rank stores the rows its peers read straight into THEIR receive
+    staging at fwd_push_offset, aggregates chunk after chunk from the staged slices; backward partials go to the
+    owner's gradient staging at bwd_push_offset and are added in send_rows_all order."""
+    g = golden
+    if g.P == 1:
+        pytest.skip("single partition: nothing to exchange")
+    L = _lib.load()
+    P = g.P
+    ranks = [_Rank(g, r) for r in range(P)]
+    try:
+        for a in ranks:
+            for j, b in enumerate(ranks):
+                assert L.nts_exchange_plan_set_peer_needs(a.plan, j, _u32p(b.counts), _u32p(b.rows)) == 0
+            assert L.nts_exchange_plan_finalize(a.plan) == 0, L.nts_last_error()
+        views = [a.view() for a in ranks]
+        po = g.partition_offset.astype(np.int64)
+        X = [g.mat(r, "X").astype(np.float32) for r in range(P)]
+        G = [g.mat(r, "G").astype(np.float32) for r in range(P)]
+
+        def offs(counts, skip):
+            o = np.zeros(P + 1, dtype=np.int64)
+            for i in range(P):
+                o[i + 1] = o[i] + (0 if i == skip else int(counts[i]))
+            return o
+
+        recv_offs = [offs(views[r]["need_count"], r) for r in range(P)]
+        srecv_offs = [offs(views[r]["send_count"], r) for r in range(P)]
+        # ---- forward pushes: NaN-filled windows prove every slot is written exactly where it is read
+        window = [np.full((views[r]["recv_total"], g.F), np.nan, dtype=np.float32) for r in range(P)]
+        for p in range(P):
+            v = views[p]
+            for j in range(P):
+                if j == p:
+                    continue
+                rows = v["send_rows_all"][srecv_offs[p][j]:srecv_offs[p][j + 1]].astype(np.int64)
+                o = int(v["fwd_push_offset"][j])
+                assert o == recv_offs[j][p]
+                window[j][o:o + rows.shape[0]] = X[p][rows]
+        for r in range(P):
+            assert not np.isnan(window[r]).any()
+            Vp = int(po[r + 1] - po[r])
+            lc = ranks[r].chunks[r]
+            y = np.zeros((Vp, g.F))
+            if lc["meta"][0]:
+                y += _segment_sum(lc["column_offset"], lc["row_indices"].astype(np.int64) - po[r],
+                                  lc["edge_weight_forward"], X[r], Vp)
+            for s in range(1, P):                      # ring order of the engine
+                i = (r + s) % P
+                c = ranks[r].chunks[i]
+                n_i = int(views[r]["need_count"][i])
+                if not c["meta"][0]:
+                    continue
+                slots, _ = _plan_chunk(ranks[r].plan, i, c["meta"][0], n_i)
+                assert slots.max() < n_i
+                y += _segment_sum(c["column_offset"], slots, c["edge_weight_forward"],
+                                  window[r][recv_offs[r][i]:recv_offs[r][i + 1]], Vp)
+            _close(y, g.mat(r, "gcn_Y"))
+        # ---- backward pushes
+        gwin = [np.full((views[r]["send_total"], g.F), np.nan) for r in range(P)]
+        for p in range(P):
+            for i in range(P):
+                if i == p:
+                    continue
+                c = ranks[p].chunks[i]
+                n_i = int(views[p]["need_count"][i])
+                _, offc = _plan_chunk(ranks[p].plan, i, c["meta"][0], n_i)
+                part = _segment_sum(offc, c["column_indices"].astype(np.int64) - po[p], c["edge_weight_backward"],
+                                    G[p], n_i) if c["meta"][0] else np.zeros((n_i, g.F))
+                o = int(views[p]["bwd_push_offset"][i])
+                assert o == srecv_offs[i][p]
+                gwin[i][o:o + n_i] = part
+        for r in range(P):
+            assert not np.isnan(gwin[r]).any()
+            Vp = int(po[r + 1] - po[r])
+            lc = ranks[r].chunks[r]
+            dx = np.zeros((Vp, g.F))
+            if lc["meta"][0]:
+                dx += _segment_sum(lc["row_offset"], lc["column_indices"].astype(np.int64) - po[r],
+                                   lc["edge_weight_backward"], G[r], Vp)
+            np.add.at(dx, views[r]["send_rows_all"].astype(np.int64), gwin[r])
+            _close(dx, g.mat(r, "gcn_dX"))
     finally:
         for a in ranks:
             a.close()

@@ -1,7 +1,12 @@
-"""CUDA data path of the distributed fused aggregation on 2 (or 4) GPUs of one box, both transports ("nccl"
-all-to-all and "p2p" peer-memory pull), against the golden vectors of the reference run at the same P.
-Skipped when fewer GPUs are visible (the round-end single-GPU run); run with `gpurun --gpus 2 -- pytest -m gpu
-tests/test_multi_gpu.py`."""
+"""CUDA data path of the distributed fused aggregation against the golden vectors of the reference run at the same P.
+
+  * test_distributed_fused_aggregation: one rank per GPU on 2 (or 4) GPUs of one box, both transports ("nccl" =
+    one all-to-all + merged remote chunk, "p2p" = the peer-memory push engine, csrc/nts_exchange.cu).  Skipped when fewer GPUs are
+    visible; run with `gpurun --gpus 2 -- pytest -m gpu tests/test_multi_gpu.py`.
+  * test_p2p_engine_ranks_sharing_one_gpu: the SAME engine, flag protocol and CUDA-IPC windows with 2 / 3 / 4 ranks
+    as separate processes time-slicing ONE GPU (control plane over gloo), so the single-GPU round-end run exercises
+    the cross-process epoch protocol, window double-buffering, empty partitions and the planned-aggregation path
+    under real concurrency too."""
 import os
 import sys
 
@@ -90,6 +95,87 @@ def test_distributed_fused_aggregation(case, world, transport):
     try:
         for _ in range(world):
             results.append(q.get(timeout=300))
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for rank, msg in sorted(results):
+        assert msg == "ok", "rank %d: %s" % (rank, msg)
+
+
+def _shared_gpu_worker(rank, world, port, case, plan_all, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["NTS_EXCHANGE_TIMEOUT_MS"] = "120000"   # ranks time-slice one GPU: waits are long but bounded
+    if plan_all:
+        os.environ["NTS_EXCHANGE_PLAN_MIN_EDGES"] = "1"  # every chunk through nts_gather_plan (tuned slab count)
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from neutronstarlite_b200 import ops
+        from neutronstarlite_b200.exchange import GpuExchange
+        from neutronstarlite_b200.graph import HostGraph, PartitionedGraph
+        z = np.load(os.path.join(GOLD, case))
+        V, E, P, F = (int(x) for x in z["case"])
+        pg = PartitionedGraph(HostGraph(z["edges"], V), P, rank).generate_all(device=dev, dist=True)
+        ex = GpuExchange(pg, transport="p2p")
+        op = ops.ForwardGPUfuseOp(pg, None, exchange=ex)
+        x = torch.from_numpy(z["r%d/X" % rank].reshape(-1, F)).to(dev)
+        g = torch.from_numpy(z["r%d/G" % rank].reshape(-1, F)).to(dev)
+        ref_y = z["r%d/gcn_Y" % rank].reshape(-1, F)
+        ref_dx = z["r%d/gcn_dX" % rank].reshape(-1, F)
+        for it in range(4):  # > n_buffers epochs: the consumed-flag wait of the push kernel is exercised
+            y = op.forward(x)
+            dx = op.backward(g)
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(y.cpu().numpy(), ref_y, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(dx.cpu().numpy(), ref_dx, rtol=1e-4, atol=2e-5)
+        # a wider matrix through the same engine: the window is re-reserved (release -> barrier -> reallocate)
+        F2 = 602
+        gen = torch.Generator().manual_seed(3)
+        Xg = torch.rand((V, F2), generator=gen) * 2 - 1
+        po = pg.partition_offset
+        lo, hi = int(po[rank]), int(po[rank + 1])
+        y2 = op.forward(Xg[lo:hi].contiguous().to(dev))
+        dx2 = op.backward(Xg[lo:hi].contiguous().to(dev))
+        torch.cuda.synchronize()
+        pg1 = PartitionedGraph(HostGraph(z["edges"], V), 1, 0).generate_all(device=dev)
+        one = ops.ForwardSingleGPUfuseOp(pg1)
+        y_full = one.forward(Xg.to(dev))
+        dx_full = one.backward(Xg.to(dev))
+        torch.testing.assert_close(y2, y_full[lo:hi], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(dx2, dx_full[lo:hi], rtol=1e-4, atol=2e-5)
+        dist.barrier()
+        ex.close()
+        q.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %r\n%s" % (exc, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+SHARED = [("synth9k_P2_F2.npz", 2, False), ("synth9k_P3_F2.npz", 3, True), ("cora_self_P4_F2.npz", 4, False),
+          ("cora_self_P2_F4.npz", 2, True)]
+
+
+@pytest.mark.parametrize("case,world,plan_all", SHARED)
+def test_p2p_engine_ranks_sharing_one_gpu(case, world, plan_all):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    port = 29900 + (hash((case, world)) % 90)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shared_gpu_worker, args=(r, world, port, case, plan_all, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    try:
+        for _ in range(world):
+            results.append(q.get(timeout=420))
     finally:
         for p in procs:
             p.join(timeout=30)
