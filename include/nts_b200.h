@@ -280,6 +280,15 @@ int nts_scatter_add_rows(float *dst, const float *src, const nts_vid_t *rows, nt
 int nts_scatter_add_rows_atomic(float *dst, const float *src, const nts_vid_t *rows, nts_vid_t n_rows,
                                 nts_vid_t feature_size, void *stream);
 
+/* ---- parameter update ------------------------------------------------------------------------------------
+ * Parameter::learnC2G_with_decay_Adam (core/NtsScheduler.hpp:774-781) as ONE kernel, in place on W / M / V:
+ *   W_g = W*weight_decay + grad;  M = beta1*M + (1-beta1)*W_g;  V = beta2*V + (1-beta2)*W_g*W_g;
+ *   W  -= alpha * M / (sqrt(V) + epsilon)
+ * alpha / beta1 / beta2 are the CURRENT values of the reference's schedule (Parameter::next(), :727-736).  `grad` is the
+ * all-reduced gradient (Parameter::all_reduce_to_gradient, :719-722 - ncclAllReduce here instead of .cpu() + MPI). */
+int nts_adam_update(float *W, float *M, float *V, const float *grad, uint64_t n, float weight_decay, float beta1,
+                    float beta2, float alpha, float epsilon, void *stream);
+
 /* ---- peer memory (CUDA IPC) for the NVLink exchange ------------------------------------------------------ */
 #define NTS_IPC_HANDLE_BYTES 64
 int nts_ipc_get_handle(void *device_ptr, unsigned char handle[NTS_IPC_HANDLE_BYTES]);

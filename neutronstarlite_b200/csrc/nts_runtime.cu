@@ -3,6 +3,7 @@
 // CUDA-IPC peer mappings and system-scope flag signalling for the NVLink exchange.
 #include "nts_common.cuh"
 
+#include <algorithm>
 #include <atomic>
 
 namespace nts {
@@ -50,6 +51,25 @@ __global__ void signal_wait_kernel(const uint32_t *flag, uint32_t value) {
     if (v < value)
       __nanosleep(200);
   } while (v < value);
+}
+
+// Parameter::learnC2G_with_decay_Adam (core/NtsScheduler.hpp:774-781) in one pass: the reference issues six
+// element-wise libtorch ops (each a kernel and a temporary); same arithmetic, same order of operations per element:
+//   W_g = W * weight_decay + grad;  M = beta1*M + (1-beta1)*W_g;  V = beta2*V + (1-beta2)*W_g*W_g;
+//   W   = W - alpha * M / (sqrt(V) + epsilon)
+__global__ void adam_update_kernel(float *__restrict__ W, float *__restrict__ M, float *__restrict__ V,
+                                   const float *__restrict__ grad, uint64_t n, float weight_decay, float beta1,
+                                   float beta2, float alpha, float epsilon) {
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float w = W[i];
+    const float wg = __fadd_rn(__fmul_rn(w, weight_decay), grad[i]);
+    const float m = __fadd_rn(__fmul_rn(beta1, M[i]), __fmul_rn(omb1, wg));
+    const float v = __fadd_rn(__fmul_rn(beta2, V[i]), __fmul_rn(__fmul_rn(omb2, wg), wg));
+    M[i] = m;
+    V[i] = v;
+    W[i] = __fsub_rn(w, __fdiv_rn(__fmul_rn(alpha, m), __fadd_rn(__fsqrt_rn(v), epsilon)));
+  }
 }
 
 } // namespace nts
@@ -225,6 +245,17 @@ int nts_ipc_close_handle(void *peer_ptr) {
     NTS_CUDA_OK(cudaIpcCloseMemHandle(peer_ptr));
   return 0;
 }
+int nts_adam_update(float *W, float *M, float *V, const float *grad, uint64_t n, float weight_decay, float beta1,
+                    float beta2, float alpha, float epsilon, void *stream) {
+  if (n == 0)
+    return 0;
+  NTS_ARG_CHECK(W && M && V && grad, "null pointer passed to nts_adam_update");
+  const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sm_count() * 8);
+  adam_update_kernel<<<blocks, 256, 0, as_stream(stream)>>>(W, M, V, grad, n, weight_decay, beta1, beta2, alpha, epsilon);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
 int nts_signal_set(uint32_t *flag, uint32_t value, void *stream) {
   NTS_ARG_CHECK(flag, "null flag");
   signal_set_kernel<<<1, 1, 0, as_stream(stream)>>>(flag, value);

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -28,10 +29,13 @@ class Parameter:
         self.M = torch.zeros((w, h), dtype=torch.float32, device=device)
         self.V = torch.zeros((w, h), dtype=torch.float32, device=device)
         self.W_gradient = None
-        self.alpha = alpha
-        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
-        self.alpha_t, self.beta1_t, self.beta2_t = alpha, beta1, beta2
-        self.weight_decay = weight_decay
+        # the reference keeps every hyper-parameter in `ValueType` = float and does the schedule arithmetic in float
+        # (1 - 0.999f != 0.001: a 1.3e-5 relative difference in V that the golden vectors of tests/test_adam.py see)
+        f32 = np.float32
+        self.alpha = f32(alpha)
+        self.beta1, self.beta2, self.epsilon = f32(beta1), f32(beta2), f32(epsilon)
+        self.alpha_t, self.beta1_t, self.beta2_t = f32(alpha), f32(beta1), f32(beta2)
+        self.weight_decay = f32(weight_decay)
         self.curr_epoch = 0
         self.decay_rate, self.decay_epoch = 1, -1
 
@@ -46,7 +50,7 @@ class Parameter:
 
     def all_reduce_to_gradient(self, grad):
         """SUM (not mean) over ranks, NtsScheduler.hpp:719-722 -> comm/network.h:198-203."""
-        self.W_gradient = grad.detach().clone()
+        self.W_gradient = grad.detach().clone().contiguous()
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.W_gradient, op=dist.ReduceOp.SUM)
 
@@ -54,21 +58,33 @@ class Parameter:
         """NtsScheduler.hpp:727-736."""
         if self.decay_epoch != -1 and self.curr_epoch != 0 and self.curr_epoch % self.decay_epoch == 0:
             self.alpha_t *= self.decay_rate
-        self.alpha = self.alpha_t * math.sqrt(1 - self.beta2) / (1 - self.beta1)
-        self.beta1 *= self.beta1_t
-        self.beta2 *= self.beta2_t
+        one = np.float32(1)
+        self.alpha_t = np.float32(self.alpha_t)
+        self.alpha = np.float32(self.alpha_t * np.sqrt(one - self.beta2) / (one - self.beta1))
+        self.beta1 = np.float32(self.beta1 * self.beta1_t)
+        self.beta2 = np.float32(self.beta2 * self.beta2_t)
         self.curr_epoch += 1
 
     def forward(self, x):
         return x.mm(self.W)
 
     def learn_with_decay_Adam(self):
-        """learnC2G_with_decay_Adam, NtsScheduler.hpp:774-781."""
+        """learnC2G_with_decay_Adam, NtsScheduler.hpp:774-781.  On the GPU: ONE fused kernel (nts_adam_update)
+        instead of the reference's six element-wise libtorch ops; the torch expression below is the host mirror
+        used by the CPU tests (same arithmetic, pinned to the reference's golden vectors in tests/test_adam.py)."""
         with torch.no_grad():
-            W_g = self.W * self.weight_decay + self.W_gradient
-            self.M = self.beta1 * self.M + (1 - self.beta1) * W_g
-            self.V = self.beta2 * self.V + (1 - self.beta2) * W_g * W_g
-            self.W -= self.alpha * self.M / (torch.sqrt(self.V) + self.epsilon)
+            if self.W.is_cuda:
+                from . import _lib
+                _lib.call("nts_adam_update", self.W.data_ptr(), self.M.data_ptr(), self.V.data_ptr(),
+                          self.W_gradient.data_ptr(), self.W.numel(), float(self.weight_decay), float(self.beta1),
+                          float(self.beta2), float(self.alpha), float(self.epsilon),
+                          torch.cuda.current_stream().cuda_stream)
+                return
+            one = np.float32(1)
+            W_g = self.W * float(self.weight_decay) + self.W_gradient
+            self.M = float(self.beta1) * self.M + float(one - self.beta1) * W_g
+            self.V = float(self.beta2) * self.V + float(one - self.beta2) * W_g * W_g
+            self.W -= float(self.alpha) * self.M / (torch.sqrt(self.V) + float(self.epsilon))
 
     def zero_grad(self):
         self.W.grad = None

@@ -119,7 +119,38 @@ def run_case(name, edges, V, P, F, keep_copy_only, threads):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def run_adam(steps=8):
+    """Parameter / Adam golden vectors (core/NtsScheduler.hpp:639-791 driven as toolkits/GCN.hpp:209-215 does):
+    tests/golden/adam/adam_ref.npz - kept in a sub-directory, the top-level *.npz files are graph cases."""
+    sys.path.insert(0, HERE)
+    from run_ref import launch
+    work = tempfile.mkdtemp(prefix="nts_gold_adam_")
+    try:
+        cfg = os.path.join(work, "case.cfg")
+        write_cfg(cfg, os.path.join(work, "none.edge"), 16)
+        out = os.path.join(work, "out")
+        os.makedirs(out)
+        rc = launch(1, [DRIVER, cfg, out, "adam", str(steps)], threads=1, quiet=True)
+        if rc != 0:
+            raise RuntimeError("reference driver (adam) failed rc=%d" % rc)
+        w, h, n = (int(x) for x in np.fromfile(os.path.join(out, "r0_adam_meta.bin"), dtype=np.int64))
+        data = {"meta": np.array([w, h, n], dtype=np.int64),
+                "hyper": np.array([0.01, 0.9, 0.999, 1e-9, 0.0001, 0.97, 4], dtype=np.float64),
+                "W0": np.fromfile(os.path.join(out, "r0_adam_W0.bin"), dtype=np.float32).reshape(w, h)}
+        for k in ("grads", "W", "M", "V"):
+            data[k] = np.fromfile(os.path.join(out, "r0_adam_%s.bin" % k), dtype=np.float32).reshape(n, w, h)
+        os.makedirs(os.path.join(GOLD, "adam"), exist_ok=True)
+        dst = os.path.join(GOLD, "adam", "adam_ref.npz")
+        np.savez_compressed(dst, **data)
+        print("wrote", dst, "%.1f KB" % (os.path.getsize(dst) / 1024))
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--adam":         # python oracle/make_golden.py --adam
+        run_adam()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--synth-only":   # python oracle/make_golden.py --synth-only 3 5
         os.makedirs(GOLD, exist_ok=True)
         syn = synth_edges()
@@ -136,6 +167,7 @@ def main():
     syn = synth_edges()
     for P in (1, 2, 3, 4, 8):                            # 3: a ring that is not a power of two
         run_case("synth9k", syn, 9216, P, 2, False, max(1, 4 // P))
+    run_adam()
 
 
 if __name__ == "__main__":

@@ -10,11 +10,15 @@
 // Modes (argv[3]):
 //   dump   - artefacts + operator results (golden vectors; Cora-sized inputs)
 //   time   - op-level timing of ForwardCPUfuseOp forward/backward (CPU baseline)
+//   adam   - the reference's Parameter (core/NtsScheduler.hpp:639-791) driven exactly as toolkits/GCN.hpp:209-215
+//            drives it (all_reduce_to_gradient -> learn..._Adam -> next) on deterministic W / gradients for <F>
+//            steps; dumps W, M, V after every step (golden vectors of the fused Adam kernel)
 //
-// usage: nts_ref_driver <cfg> <outdir> <dump|time> <F> [repeats]
+// usage: nts_ref_driver <cfg> <outdir> <dump|time|adam> <F> [repeats]
 #include "core/neutronstar.hpp"
 #include <fstream>
 #include <string>
+#include <vector>
 
 static std::string g_outdir;
 static int g_rank = 0;
@@ -45,6 +49,38 @@ int main(int argc, char **argv) {
   std::string mode = argv[3];
   int F = atoi(argv[4]);
   int repeats = argc > 5 ? atoi(argv[5]) : 3;
+
+  if (mode == "adam") {
+    const int steps = F, w = 37, h = 11;
+    Parameter *P = new Parameter(w, h, 0.01f, 0.9f, 0.999f, 1e-9f, 0.0001f); // toolkits/GCN.hpp:96-119
+    P->set_decay(0.97f, 4);                                                  // the reference stores both in `int`
+    NtsVar W0 = torch::zeros({w, h});
+    for (int i = 0; i < w * h; i++)
+      W0.data_ptr<float>()[i] = 0.1f * sinf(0.3f * (float)i);
+    P->W.set_data(W0.clone());
+    dump_tensor("adam_W0", W0);
+    std::vector<float> all_g, all_W, all_M, all_V;
+    for (int s = 0; s < steps; s++) {
+      NtsVar g = torch::zeros({w, h});
+      for (int i = 0; i < w * h; i++)
+        g.data_ptr<float>()[i] = 0.02f * cosf(0.05f * (float)(s * w * h + i)) + 0.001f * (float)(i % 7);
+      all_g.insert(all_g.end(), g.data_ptr<float>(), g.data_ptr<float>() + w * h);
+      P->all_reduce_to_gradient(g);
+      P->learnC2C_with_decay_Adam();
+      P->next();
+      NtsVar Wc = P->W.detach().contiguous(), Mc = P->M.contiguous(), Vc = P->V.contiguous();
+      all_W.insert(all_W.end(), Wc.data_ptr<float>(), Wc.data_ptr<float>() + w * h);
+      all_M.insert(all_M.end(), Mc.data_ptr<float>(), Mc.data_ptr<float>() + w * h);
+      all_V.insert(all_V.end(), Vc.data_ptr<float>(), Vc.data_ptr<float>() + w * h);
+    }
+    long meta[3] = {w, h, steps};
+    dump("adam_meta", meta, 3);
+    dump("adam_grads", all_g.data(), all_g.size());
+    dump("adam_W", all_W.data(), all_W.size());
+    dump("adam_M", all_M.data(), all_M.size());
+    dump("adam_V", all_V.data(), all_V.size());
+    return 0;
+  }
 
   Graph<Empty> *graph = new Graph<Empty>();
   graph->config->readFromCfgFile(argv[1]);
