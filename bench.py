@@ -45,9 +45,12 @@ def parse_args():
     ap.add_argument("--drop-rate", type=float, default=0.0,
                     help="both arms run DROP_RATE 0: the reference's in-place dropout trips libtorch 2.11's autograd "
                          "version check (SURVEY 8c), so its CPU arm cannot run with dropout")
-    ap.add_argument("--toolkit", default="gcn", choices=["gcn", "gcn_eager"],
+    ap.add_argument("--toolkit", default="gcn", choices=["gcn", "gcn_eager", "gat"],
                     help="gcn = toolkits/GCN.hpp order (aggregate, then GEMM: the headline config); gcn_eager = "
-                         "toolkits/GCN_EAGER*.hpp order (GEMM, then aggregate the narrow result) - opt-in")
+                         "toolkits/GCN_EAGER*.hpp order (GEMM, then aggregate the narrow result) - opt-in; gat = config D "
+                         "of BASELINE.json: 3-layer 8-head GAT on the fused attention aggregation (K7), 1 GPU")
+    ap.add_argument("--layers", default=None, help="override LAYERS, e.g. 602-64-64-41 (the gat default on reddit)")
+    ap.add_argument("--heads", type=int, default=8)
     ap.add_argument("--cpu-sample-div", type=int, default=0,
                     help="CPU arm runs a 1/div scale model of the workload (V/div vertices, E/div edges, same degree "
                          "law, mean degree and widths); 0 = pick div from a probe so the run fits --cpu-budget-s")
@@ -243,6 +246,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     V, E_rand, layers = synth.WORKLOADS[args.workload]
+    if args.toolkit == "gat" and args.layers is None:
+        layers = [layers[0], 64, 64, layers[-1]]           # config D: hidden layers of 8 heads x 8
+    if args.layers:
+        layers = [int(x) for x in args.layers.split("-")]
     E_total = E_rand + V
 
     # ------------------------------------------------------------------ reference arm: CPU only, rank 0 only
@@ -277,7 +284,7 @@ def main():
     from neutronstarlite_b200 import _lib, ops
     from neutronstarlite_b200.exchange import GpuExchange
     from neutronstarlite_b200.graph import PartitionedGraph, partition_offsets_from_out_degree
-    from neutronstarlite_b200.toolkits import GCNImpl, GCNEagerImpl
+    from neutronstarlite_b200.toolkits import GATImpl, GCNImpl, GCNEagerImpl
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -288,13 +295,23 @@ def main():
     _lib.call("nts_aggregate_set_variant", args.variant, args.edges_per_warp)
 
     # graph: every rank generates the same edge list (same seed), keeps only what it owns
-    src, dst = synth.zipf_edges(V, E_rand, dev, s=args.zipf_s)
-    out_raw = torch.bincount(src, minlength=V)
-    out_deg = out_raw.clamp(min=1)
-    in_deg = torch.bincount(dst, minlength=V).clamp_(min=1)
-    po = partition_offsets_from_out_degree(out_raw.cpu().numpy(), E_total, world)
-    pg = PartitionedGraph.from_device_edges(src, dst, V, world, rank, po, out_deg, in_deg)
-    del src, dst
+    if E_total > (1 << 29):
+        # too big to hold next to its features: two streaming passes over the same deterministic edge stream
+        # (degrees -> the reference's partition offsets -> only the edges this rank owns), SURVEY 8d config E
+        out_raw, in_raw = synth.zipf_degrees(V, E_rand, dev, s=args.zipf_s)
+        # (every vertex has its self loop, so no degree is 0; the partitioner wants the degrees with multiplicity)
+        po = partition_offsets_from_out_degree(out_raw.cpu().numpy(), E_total, world)
+        src, dst = synth.zipf_edges_owned(V, E_rand, dev, int(po[rank]), int(po[rank + 1]), s=args.zipf_s)
+        pg = PartitionedGraph.from_device_edges(src, dst, V, world, rank, po, out_raw.clamp(min=1), in_raw.clamp(min=1))
+        del src, dst, out_raw, in_raw
+    else:
+        src, dst = synth.zipf_edges(V, E_rand, dev, s=args.zipf_s)
+        out_raw = torch.bincount(src, minlength=V)
+        out_deg = out_raw.clamp(min=1)
+        in_deg = torch.bincount(dst, minlength=V).clamp_(min=1)
+        po = partition_offsets_from_out_degree(out_raw.cpu().numpy(), E_total, world)
+        pg = PartitionedGraph.from_device_edges(src, dst, V, world, rank, po, out_deg, in_deg)
+        del src, dst
     torch.cuda.empty_cache()
     v0, v1 = int(po[rank]), int(po[rank + 1])
     feats, labels, mask = synth.features_labels_mask(V, layers[0], layers[-1], dev, rows=(v0, v1))
@@ -319,12 +336,38 @@ def main():
             ex = GpuExchange(pg, transport=transport)
         op_kwargs["exchange"] = ex
     eager = args.toolkit == "gcn_eager"
-    model = (GCNEagerImpl if eager else GCNImpl)(pg, layers, feats, labels, mask, drop_rate=args.drop_rate,
-                                                  op_kwargs=op_kwargs)
+    gat = args.toolkit == "gat"
     n_layers = len(layers) - 1
+    if gat:
+        if world != 1:
+            raise SystemExit("bench.py: --toolkit gat is config D (1 GPU)")
+        # whole-partition CSC + MirrorIndex of the edge operators (P = 1: chunk 0 is the whole partition,
+        # core/PartitionedGraph.hpp:105-143,295-305)
+        c0 = pg.graph_chunks[0]
+        pg.owned_vertices, pg.owned_edges = V, c0.edge_size
+        pg.column_offset_gpu, pg.row_indices_gpu = c0.column_offset_gpu, c0.row_indices_gpu
+        has_src = torch.zeros(V + 1, dtype=torch.int32, device=dev)
+        ro = c0.row_offset_gpu.long()
+        has_src[1:] = (ro[1:] > ro[:-1]).to(torch.int32)
+        pg.mirror_index_gpu = torch.cumsum(has_src, 0).to(torch.int32)
+        pg.owned_mirrors = int(pg.mirror_index_gpu[-1].item())
+        del has_src, ro
+        gat_model = GATImpl(pg, layers, feats, labels, mask, heads=args.heads, exchange=GpuExchange(pg),
+                            fused_kernel=True, two_pass_backward=True)
+
+        class _AsGcn:                      # same (loss, acc) return and X[0] slot as the GCN toolkits
+            X = gat_model.X
+
+            @staticmethod
+            def run_epoch():
+                return gat_model.run_epoch(), None
+        model = _AsGcn
+    else:
+        model = (GCNEagerImpl if eager else GCNImpl)(pg, layers, feats, labels, mask, drop_rate=args.drop_rate,
+                                                      op_kwargs=op_kwargs)
     # aggregation calls per epoch: GCN.hpp never back-propagates its first graph op (SURVEY 8 note) -> L + (L-1);
-    # the eager order starts with an NN op, so all L graph ops have a backward -> 2L
-    agg_calls = float(2 * n_layers if eager else 2 * n_layers - 1)
+    # the eager order and GAT start with an NN op, so all L graph ops have a backward -> 2L
+    agg_calls = float(2 * n_layers if (eager or gat) else 2 * n_layers - 1)
 
     def barrier():
         if world > 1:
@@ -417,10 +460,12 @@ def main():
                "h2d_bytes_per_step": int(hb.item()), "d2h_bytes_per_step": 4 * world}
 
     # ---- roofline of the dominant kernel: layer-0 forward aggregation (widest F), this rank's launches
-    F0 = layers[1] if eager else layers[0]
-    k = ksum.get(("fwd", F0))
+    F0 = layers[1] if (eager or gat) else layers[0]
+    k = ksum.get(("gat_fwd" if gat else "fwd", F0))
     roof = None
-    if k and k["ms"] > 0:
+    if gat and k and k["ms"] > 0:
+        roof = _gat_roofline(k, ksum, F0, args.heads)
+    elif k and k["ms"] > 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -454,7 +499,7 @@ def main():
                for (tag, F), d in ksum.items()}
 
     ref_gpu = None
-    if world == 1 and not args.no_ref_gpu:
+    if world == 1 and not args.no_ref_gpu and not gat:
         try:
             ref_gpu = reference_gpu_kernels(pg, feats, layers, torch)
         except Exception as exc:  # baseline only: never fail the bench because of it
@@ -466,7 +511,7 @@ def main():
                 "note": "CUDA-event time of the aggregation launches only (rank 0), SURVEY 8d"}
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1 and not eager:   # the CPU arm is ALGORITHM:GCNCPU (gcn order)
+        if not args.no_cpu_baseline and world == 1 and not eager and not gat:   # the CPU arm is ALGORITHM:GCNCPU
             cores = usable_cores()
             div, probe = pick_cpu_sample(V, E_rand, layers, args.cpu_sample_div, min(args.cpu_budget_s, 25.0), 3, cores)
             Vs, edges = _scale_model(V, E_rand, div)
@@ -622,11 +667,37 @@ def reference_gpu_kernels(pg, feats, layers, torch):
     return out
 
 
+def _gat_roofline(k, ksum, F, H):
+    """K7 forward (segment_gather_sum_kernel in head mode 2): per edge one slot index, one [H] source-score row and
+    one F-wide mirror row; per destination its F-wide output and three [H] rows (score, max, sum)."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    b_alg = k["edges"] * (4 + 4 * H + 4 * F) + k["rows"] * (4 * F + 12 * H) + (k["rows"] + k["calls"]) * 4
+    achieved = b_alg / (k["ms"] * 1e-3) / 1e9
+    out = {"bound": "hbm", "kernel": "segment_gather_sum_kernel<HM=2> (fused GAT attention forward, F=%d, %d heads)" % (F, H),
+           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+           "frac_note": "algorithmic bytes / time; > 1 means L1/L2 reuse of the gathered rows", "traffic": None,
+           "launches": k["calls"], "avg_ms_per_launch": k["ms"] / k["calls"],
+           "algorithmic_bytes_per_launch": b_alg / k["calls"]}
+    kb = ksum.get(("gat_bwd", F))
+    if kb and kb["ms"] > 0:   # two edge passes: mirror rows once, gradient rows once, 16-byte records per (dst, head)
+        bb = kb["edges"] * (4 + 4 * F) + kb["edges"] // 2 * 16 * H
+        out["backward"] = {"kernel": "gat_backward_pass_kernel x2 (dst-major + src-major)",
+                           "avg_ms_per_call": kb["ms"] / kb["calls"], "achieved": bb / (kb["ms"] * 1e-3) / 1e9,
+                           "frac": bb / (kb["ms"] * 1e-3) / 1e9 / peak}
+    return out
+
+
 def _config(args, V, E_total, layers):
     """The workload as both arms see it (identical dict in `ours` and `--impl reference`)."""
-    eager = args.toolkit == "gcn_eager"
+    eager = args.toolkit in ("gcn_eager", "gat")
     n_layers = len(layers) - 1
-    return {"workload": _workload_name(args.workload, V, E_total, layers), "toolkit": args.toolkit,
+    return {"workload": _workload_name(args.workload, V, E_total, layers, args), "toolkit": args.toolkit,
             "aggregations_per_epoch": 2 * n_layers if eager else 2 * n_layers - 1, "drop_rate": args.drop_rate,
             "zipf_s": args.zipf_s,
             "l2": "%s: features %.0f MB + graph arrays %.0f MB (all ranks), no flush between steps" % (
@@ -670,9 +741,12 @@ def _sample_text(div, Vs, Es, probe):
     return t
 
 
-def _workload_name(name, V, E, layers):
-    return "%s-shaped synthetic power-law graph: %d V, %d E (incl. self loops), 2-layer GCN %s fp32" % (
-        name, V, E, "-".join(str(x) for x in layers))
+def _workload_name(name, V, E, layers, args=None):
+    model = "%d-layer GCN" % (len(layers) - 1)
+    if args is not None and args.toolkit == "gat":
+        model = "%d-layer GAT, %d heads" % (len(layers) - 1, args.heads)
+    return "%s-shaped synthetic power-law graph: %d V, %d E (incl. self loops), %s %s fp32" % (
+        name, V, E, model, "-".join(str(x) for x in layers))
 
 
 def _ncu_traffic(F):

@@ -133,6 +133,9 @@ int nts_gather_plan_run(nts_gather_plan *plan, const float *input, float *output
                         void *stream);
 int nts_gather_plan_last_launch(const nts_gather_plan *plan, int *launches, int *grid, int *k, int *u, int *outv);
 int nts_gather_plan_set_tuning(int u, int min_blocks, int edges_per_warp); /* measurement hook, 0 = default */
+/* 0 = gathered rows through registers (default); 1 = rows staged in shared memory by per-row cp.async.bulk (TMA) into
+ * a per-warp ring, U of set_tuning = ring depth - the north star's "feature tiles via TMA", kept for measurement */
+int nts_gather_plan_set_variant(int variant);
 
 /* Same contraction with the source row taken through a slot table instead of `index - base`:
  * row = slot_of[indices[e]].  Used with MirrorIndex (core/PartitionedGraph.hpp:295-305) for the fused

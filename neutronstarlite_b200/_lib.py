@@ -58,6 +58,7 @@ SIGNATURES = {
     "nts_gather_plan_run": (_int, [_vp, _vp, _vp, _u32, _vp]),
     "nts_gather_plan_last_launch": (_int, [_vp] + [C.POINTER(_int)] * 5),
     "nts_gather_plan_set_tuning": (_int, [_int, _int, _int]),
+    "nts_gather_plan_set_variant": (_int, [_int]),
     "nts_segment_gather_sum_slots": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u64, _u32, _vp]),
     "nts_segment_gather_sum_heads": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u64, _u32, _u32, _vp]),
     "nts_aggregate_set_variant": (_int, [_int, _int]),

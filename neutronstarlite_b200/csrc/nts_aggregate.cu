@@ -151,7 +151,10 @@ __device__ __forceinline__ float att_weight(float s, float d, float m, float inv
 //                        that owns them (head of column c = c / D), loaded per lane (lanes of one head broadcast);
 //                    2 = fused GAT attention: the weight is recomputed from per-vertex scores (AttParams).
 //        For HM != 0 a lane's K chunks may belong to different heads, so weights / row constants are per chunk.
-template <int VEC, int K, int U, bool BULK, int MINB = 1, int HM = 0>
+// G    : virtual warps per warp (BULK only): rows of at most 16 vectors leave half of the lanes idle, so the warp is
+//        split into G independent groups of 32/G lanes, each with its own edge quantum and row state (the BULK
+//        variant has no warp-wide shuffles; all bookkeeping is per lane).  Used by the fused GAT layers (F = 64).
+template <int VEC, int K, int U, bool BULK, int MINB = 1, int HM = 0, int G = 1>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     segment_gather_sum_kernel(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ w,
                               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ off,
@@ -159,10 +162,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
                               uint64_t n_edges64, uint32_t F, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
                               uint32_t tile_major, uint32_t heads, AttParams att, uint32_t e_begin, uint32_t out_mod) {
   static_assert(!(HM == 1 && BULK), "[E, H] weight matrices are not bulk-staged (indices of HM 0 / 2 are)");
+  static_assert(G == 1 || (BULK && K == 1), "virtual warps need the shuffle-free variant and one chunk per lane");
   using V = typename Vec<VEC>::type;
+  constexpr uint32_t GS = 32 / G;
+  constexpr uint32_t kVW = kWarpsPerBlock * G; // (virtual) warps per CTA
   const uint32_t n_edges = (uint32_t)n_edges64;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp_in_block = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & (GS - 1);
+  const uint32_t warp_in_block = threadIdx.x / GS;
   const uint32_t nvec = F / VEC;
 
   // quantum / column tile owned by this warp.
@@ -170,10 +176,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   //   tile-major  (tile_major = 1): all quanta of tile 0 first, then tile 1, ...: at any moment the CTAs in flight
   //     touch one column slab of the feature matrix, which is sized to stay resident in the 126 MB L2.
   //     Warps per tile are padded to a multiple of the CTA size so a CTA never straddles two tiles.
-  const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp_in_block;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * kVW + warp_in_block;
   // the launch covers edges [e_begin, n_edges64) of the arrays (e_begin = off[0]; 0 except for row-range launches)
   const uint64_t n_quanta = (n_edges64 - e_begin + Q - 1) / Q;
-  const uint64_t wpt = (n_quanta + kWarpsPerBlock - 1) / kWarpsPerBlock * kWarpsPerBlock;
+  const uint64_t wpt = (n_quanta + kVW - 1) / kVW * kVW;
   const uint32_t tile = tile_major ? (uint32_t)(gwarp / wpt) : (uint32_t)(gwarp % tiles);
   const uint64_t q = tile_major ? gwarp % wpt : gwarp / tiles;
   const uint64_t e0_64 = e_begin + q * (uint64_t)Q;
@@ -185,16 +191,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   uint32_t cta_e_base = 0; // first staged edge (16-byte aligned element index)
   uint32_t bulk_bytes = 0;
   if constexpr (BULK) {
-    // CTA edge span: quanta of warps 0..kWarpsPerBlock-1
-    const uint64_t cta_w0 = (uint64_t)blockIdx.x * kWarpsPerBlock;
+    // CTA edge span: quanta of warps 0..kVW-1
+    const uint64_t cta_w0 = (uint64_t)blockIdx.x * kVW;
     const uint64_t first_q = tile_major ? cta_w0 % wpt : cta_w0 / tiles;
-    const uint64_t last_q = tile_major ? first_q + kWarpsPerBlock - 1 : (cta_w0 + kWarpsPerBlock - 1) / tiles;
+    const uint64_t last_q = tile_major ? first_q + kVW - 1 : (cta_w0 + kVW - 1) / tiles;
     uint64_t ce0 = e_begin + first_q * (uint64_t)Q;
     uint64_t ce1 = e_begin + (last_q + 1) * (uint64_t)Q;
     if (ce1 > n_edges)
       ce1 = n_edges;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    const uint32_t span_cap = kWarpsPerBlock * Q + 8; // elements reserved per array (host sizes smem to this)
+    const uint32_t span_cap = kVW * Q + 8; // elements reserved per array (host sizes smem to this)
     s_idx = reinterpret_cast<uint32_t *>(smem_raw + 16);
     s_w = reinterpret_cast<float *>(smem_raw + 16 + (size_t)span_cap * 4);
     if (ce0 < ce1) {
@@ -233,10 +239,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
   uint32_t hk[K]; // head that owns chunk k of this lane (HM != 0)
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    act[k] = (k * 32 + lane) < tile_vecs && (c0 + k * 32) < nvec;
+    act[k] = (k * GS + lane) < tile_vecs && (c0 + k * GS) < nvec;
     hk[k] = 0;
     if constexpr (HM != 0)
-      hk[k] = act[k] ? ((c0 + k * 32) * VEC) / (F / heads) : 0u;
+      hk[k] = act[k] ? ((c0 + k * GS) * VEC) / (F / heads) : 0u;
   }
 
   // first row of the quantum (overlaps with the bulk copy in flight)
@@ -274,9 +280,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
     for (int k = 0; k < K; k++) {
       if (act[k]) {
         if (whole)
-          rmw_add(o + k * 32, acc[k]);
+          rmw_add(o + k * GS, acc[k]);
         else
-          red_add(o + k * 32, acc[k]);
+          red_add(o + k * GS, acc[k]);
       }
       zero_vec(acc[k]);
     }
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 #pragma unroll
         for (int k = 0; k < K; k++) {
           if (act[k])
-            v[u][k] = ldg_vec<VEC>(p + k * 32);
+            v[u][k] = ldg_vec<VEC>(p + k * GS);
           if constexpr (HM == 1)
             wu[u][k] = act[k] ? __ldg(w + (size_t)(e + j + u) * heads + hk[k]) : 0.f;
           if constexpr (HM == 2)
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 #pragma unroll
       for (int k = 0; k < K; k++) {
         if (act[k])
-          v1[k] = ldg_vec<VEC>(p + k * 32);
+          v1[k] = ldg_vec<VEC>(p + k * GS);
         if constexpr (HM == 1)
           wj[k] = act[k] ? __ldg(w + (size_t)(e + j) * heads + hk[k]) : 0.f;
         if constexpr (HM == 2)
@@ -399,6 +405,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 struct LaunchShape {
   int vec, k, u, minb;
   uint32_t tiles, tile_vecs, tile_major, heads;
+  int g = 1;            // virtual warps per warp (fused attention on rows of <= 16 vectors)
   uint32_t e_begin = 0; // first edge of the launch (row-range launches), offsets[0]
   uint32_t out_mod = 0; // != 0: offsets index virtual rows slab * out_mod + row (slab-bucketed arrays)
 };
@@ -474,6 +481,24 @@ static int launch_shape(bool bulk, const LaunchShape &sh, const float *in, float
   if (att || sh.heads > 1) {
     if constexpr (MINB == 1) { // per-head kernels exist for the untuned occupancy points only
       g_last_smem = 0;
+      if constexpr (K == 1) {
+        if (att && bulk && sh.g == 2) { // rows of <= 16 vectors: two virtual warps per warp
+          constexpr int G2 = 2;
+          size_t span_cap = (size_t)kWarpsPerBlock * G2 * Q + 8;
+          size_t smem = 16 + 2 * span_cap * 4;
+          auto kern = segment_gather_sum_kernel<VEC, K, U, true, 1, 2, G2>;
+          NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          g_last_smem = (int)smem;
+          const uint64_t vblocks = (warps + kWarpsPerBlock * G2 - 1) / (kWarpsPerBlock * G2);
+          g_last_grid = (int)vblocks;
+          kern<<<(unsigned)vblocks, kWarpsPerBlock * 32, smem, st>>>(in, out, nullptr, idx, off, slot_of, base, n_rows,
+                                                                     n_edges, F, Q, sh.tiles, sh.tile_vecs,
+                                                                     sh.tile_major, sh.heads, *att, sh.e_begin,
+                                                                     sh.out_mod);
+          NTS_LAUNCH_CHECK();
+          return 0;
+        }
+      }
       if (att && bulk) { // fused attention with TMA-staged index tiles (no weight array to stage)
         size_t span_cap = (size_t)kWarpsPerBlock * Q + 8;
         size_t smem = 16 + 2 * span_cap * 4;
@@ -540,15 +565,19 @@ static int segment_gather_sum(const float *in, float *out, const float *w, const
     s.minb = 1;
     int budget = 40 / (s.k * s.vec);
     s.u = budget >= 8 ? 8 : (budget >= 4 ? 4 : 2);
+    if (att && s.k == 1 && s.tiles == 1 && F / s.vec <= 16 && !s.tile_major && !getenv("NTS_AGG_NO_SUBWARP"))
+      s.g = 2;
   }
   // edges per warp: multiple of 32; shrink for small inputs so the grid still fills 148 SMs
-  uint32_t Q = g_edges_per_warp > 0 ? (uint32_t)g_edges_per_warp : 512u;
+  uint32_t Q = g_edges_per_warp > 0 ? (uint32_t)g_edges_per_warp : 512u / (uint32_t)s.g;
   if (g_edges_per_warp <= 0) {
     const uint64_t want_warps = (uint64_t)sm_count() * 64;
     while (Q > 32 && ((n_edges - e_begin + Q - 1) / Q) * s.tiles < want_warps)
       Q >>= 1;
   }
   Q = (Q + 31u) & ~31u;
+  if (s.g > 1 && Q * s.g > 1024) // the CTA's staged index span must keep fitting shared memory
+    Q = (1024u / s.g) & ~31u;
   int variant = g_variant == 0 ? 2 : g_variant; // measured on B200: bulk-staged indices are ~15-20% faster
   bool bulk = variant == 2 && (att || heads <= 1); // [E, H] weight matrices are not bulk-staged
   // the bulk copies need 16-byte aligned index/weight arrays (cudaMalloc gives 256)

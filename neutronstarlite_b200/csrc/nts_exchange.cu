@@ -236,15 +236,18 @@ static int launch_push(nts_exchange *ex, const PushArgs &a, const float *src, ui
 // aggregation of one chunk direction: preprocessed plan for big chunks, the plain kernel otherwise
 static int aggregate_chunk(nts_exchange *ex, int i, bool forward, const float *in, float *out, uint32_t F,
                            cudaStream_t st) {
+  // chunk p is the local one: its "slots" are the global source ids of my own partition (base = dst_start) and its
+  // "compact" row offsets are the plain row_offset over all my vertices
   const nts_exchange_chunk &c = ex->chunks[i];
-  const uint32_t n_rows = forward ? ex->d.owned_vertices : ex->need_count[i];
-  const uint32_t gather_rows = forward ? ex->need_count[i] : ex->d.owned_vertices;
+  const bool local = i == ex->p;
+  const uint32_t n_rows = (forward || local) ? ex->d.owned_vertices : ex->need_count[i];
+  const uint32_t gather_rows = (forward && !local) ? ex->need_count[i] : ex->d.owned_vertices;
   if (!c.edges || !n_rows)
     return 0;
   const nts_vid_t *off = forward ? c.column_offset : c.row_offset_compact;
   const nts_vid_t *idx = forward ? c.slots : c.column_indices;
   const float *w = forward ? c.weight_forward : c.weight_backward;
-  const uint32_t base = forward ? 0u : ex->d.dst_start;
+  const uint32_t base = (forward && !local) ? 0u : ex->d.dst_start;
   if (c.edges >= ex->plan_min_edges) {
     std::vector<std::pair<int, nts_gather_plan *>> &plans = (forward ? ex->plan_fwd : ex->plan_bwd)[i];
     nts_gather_plan *pl = nullptr;
@@ -295,6 +298,16 @@ nts_exchange *nts_exchange_create(const nts_exchange_desc *desc) {
     ex->fwd_push_off[i] = desc->fwd_push_offset[i];
     ex->bwd_push_off[i] = desc->bwd_push_offset[i];
     ex->chunks[i] = desc->chunks[i];
+  }
+  {
+    nts_exchange_chunk &c = ex->chunks[p];
+    c.column_offset = desc->local_column_offset;
+    c.slots = desc->local_row_indices;
+    c.weight_forward = desc->local_weight_forward;
+    c.row_offset_compact = desc->local_row_offset;
+    c.column_indices = desc->local_column_indices;
+    c.weight_backward = desc->local_weight_backward;
+    c.edges = desc->local_edges;
   }
   ex->recv_offs.assign(P + 1, 0), ex->srecv_offs.assign(P + 1, 0);
   for (int i = 0; i < P; i++) {
@@ -503,9 +516,7 @@ static int forward_impl(nts_exchange *ex, const float *x, float *y, nts_vid_t F,
   NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
   NTS_TRY(launch_push(ex, a, x, F, ex->comm));
   // ---- main stream: local chunk, then the remote chunks as their rows arrive
-  NTS_TRY(nts_gather_by_dst_from_src(x, y, d.local_weight_forward, d.local_row_indices, d.local_column_offset, d.dst_start,
-                                     d.dst_start + d.owned_vertices, d.dst_start, d.dst_start + d.owned_vertices,
-                                     d.local_edges, d.owned_vertices, F, 1, st));
+  NTS_TRY(aggregate_chunk(ex, p, true, x, y, F, st));
   for (int s = 1; s < P; s++) {
     const int i = (p + s) % P;
     wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, 1u << i, epoch, ex->timeout_ns, ex->err_dev);
@@ -559,9 +570,7 @@ static int backward_impl(nts_exchange *ex, const float *g, float *dx, nts_vid_t 
     NTS_TRY(launch_push(ex, a, ex->bsend, F, ex->comm));
   }
   // ---- local chunk overlaps with the pushes; then everything the peers computed for my rows
-  NTS_TRY(nts_gather_by_src_from_dst(g, dx, d.local_weight_backward, d.local_row_offset, d.local_column_indices,
-                                     d.dst_start, d.dst_start + d.owned_vertices, d.dst_start,
-                                     d.dst_start + d.owned_vertices, d.local_edges, d.owned_vertices, F, 1, st));
+  NTS_TRY(aggregate_chunk(ex, p, false, g, dx, F, st));
   uint32_t mask = 0;
   for (int j = 0; j < P; j++)
     if (j != p)

@@ -49,7 +49,7 @@ struct nts_gather_plan {
 
 namespace nts {
 
-static int g_plan_u = 0, g_plan_minb = 0, g_plan_q = 0; // measurement hooks (NTS_PLAN_TUNE="U,MINB[,Q]"), 0 = default
+static int g_plan_u = 0, g_plan_minb = 0, g_plan_q = 0, g_plan_variant = 0; // measurement hooks (NTS_PLAN_TUNE="U,MINB[,Q]"), 0 = default
 
 // ---- plan construction kernels -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t plan_find_row(const uint32_t *__restrict__ off, uint32_t n_rows, uint32_t e) {
@@ -197,16 +197,21 @@ __device__ __forceinline__ void flush_chunk(float *__restrict__ orow, uint32_t c
 // U    : edges whose K loads are issued before any FMA (U*K independent 16-byte loads per lane)
 // OUTV : floats per output store (4 when F % 4 == 0 and the output is 16-byte aligned, else 2 or 1)
 // MINB : __launch_bounds__ minimum CTAs per SM
+// G    : virtual warps per warp.  Rows of at most 16 / 8 float4 (F <= 64 / 32) would leave half / three quarters of
+//        the lanes idle, so a warp is split into G independent groups of 32/G lanes, each with its own edge quantum,
+//        row bookkeeping and accumulators (the kernel has no warp-wide shuffles: all state is per lane already).
 // Warp g owns the edge quantum [e_begin + q*Q, ...) of column tile t (g = q*tiles + t); the (row, weight) pairs of the
 // CTA's edge span are staged in shared memory by one cp.async.bulk, completion on an mbarrier.
-template <int K, int U, int OUTV, int MINB>
+template <int K, int U, int OUTV, int MINB, int G = 1>
 __global__ void __launch_bounds__(kPlanWarps * 32, MINB)
     planned_gather_sum_kernel(const float4 *__restrict__ in, uint32_t ld4, float *__restrict__ out, uint32_t F,
                               const uint2 *__restrict__ pairs, const uint32_t *__restrict__ off, uint32_t n_rows,
                               uint32_t e_begin, uint32_t e_end, uint32_t Q, uint32_t tiles, uint32_t tile_vecs) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp_in_block = threadIdx.x >> 5;
-  const uint64_t gwarp = (uint64_t)blockIdx.x * kPlanWarps + warp_in_block;
+  static_assert(G == 1 || K == 1, "virtual warps are for rows narrower than a warp");
+  constexpr uint32_t GS = 32 / G;                       // lanes per virtual warp
+  const uint32_t lane = threadIdx.x & (GS - 1);         // lane within the virtual warp
+  const uint32_t vwarp_in_block = threadIdx.x / GS;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * (kPlanWarps * G) + vwarp_in_block;
   const uint32_t tile = (uint32_t)(gwarp % tiles);
   const uint64_t q = gwarp / tiles;
   const uint64_t e0_64 = e_begin + q * (uint64_t)Q;
@@ -216,9 +221,9 @@ __global__ void __launch_bounds__(kPlanWarps * 32, MINB)
   uint2 *s_pair = reinterpret_cast<uint2 *>(smem_raw + 16);
   uint32_t cta_e_base = 0, bulk_bytes = 0;
   {
-    const uint64_t cta_w0 = (uint64_t)blockIdx.x * kPlanWarps;
+    const uint64_t cta_w0 = (uint64_t)blockIdx.x * (kPlanWarps * G);
     const uint64_t first_q = cta_w0 / tiles;
-    const uint64_t last_q = (cta_w0 + kPlanWarps - 1) / tiles;
+    const uint64_t last_q = (cta_w0 + kPlanWarps * G - 1) / tiles;
     uint64_t ce0 = e_begin + first_q * (uint64_t)Q;
     uint64_t ce1 = e_begin + (last_q + 1) * (uint64_t)Q;
     if (ce1 > e_end)
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kPlanWarps * 32, MINB)
   bool act[K];
 #pragma unroll
   for (int k = 0; k < K; k++)
-    act[k] = (k * 32 + lane) < tile_vecs && (c0 + k * 32) < ld4;
+    act[k] = (k * GS + lane) < tile_vecs && (c0 + k * GS) < ld4;
 
   uint32_t row = plan_find_row(off, n_rows, e0);
   uint32_t row_end = __ldg(off + row + 1);
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(kPlanWarps * 32, MINB)
     float *orow = out + (size_t)row * F;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const uint32_t col = (c0 + k * 32) * 4;
+      const uint32_t col = (c0 + k * GS) * 4;
       if (act[k] && col < F) {
         if (whole)
           flush_chunk<OUTV, false>(orow, col, F, acc[k]);
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(kPlanWarps * 32, MINB)
 #pragma unroll
       for (int k = 0; k < K; k++)
         if (act[k])
-          v[u][k] = __ldg(p + k * 32);
+          v[u][k] = __ldg(p + k * GS);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(kPlanWarps * 32, MINB)
 #pragma unroll
     for (int k = 0; k < K; k++)
       if (act[k])
-        v1[k] = __ldg(p + k * 32);
+        v1[k] = __ldg(p + k * GS);
     if (e >= row_end)
       advance(e);
 #pragma unroll
@@ -338,16 +343,188 @@ __global__ void __launch_bounds__(kPlanWarps * 32, MINB)
   flush(row_started_inside && row_end <= e1);
 }
 
+struct PlanShape;
+// ---- experiment the north star asks for: feature ROWS staged in shared memory by TMA ----------------------------------
+// Same work split and row bookkeeping, but the gathered row never passes through registers on its way in: lane 0 of
+// each warp issues one cp.async.bulk (SASS UBLKCP) per edge that copies the row's tile (16-byte aligned thanks to the
+// padded workspace) into a per-warp ring of STAGES shared-memory buffers, completion on one mbarrier per stage; the
+// warp waits, reads its chunks with 16-byte LDS, accumulates, and re-arms the stage for edge e + STAGES.
+// Kept as variant 1 of nts_gather_plan_set_variant for measurement (profiles/): bulk copies bypass L1, which serves
+// the hub rows of a skewed graph, and every gathered byte still crosses the shared-memory data stage once.
+template <int K, int STAGES, int OUTV, int MINB>
+__global__ void __launch_bounds__(kPlanWarps * 32, MINB)
+    planned_gather_sum_tma_kernel(const float4 *__restrict__ in, uint32_t ld4, float *__restrict__ out, uint32_t F,
+                                  const uint2 *__restrict__ pairs, const uint32_t *__restrict__ off, uint32_t n_rows,
+                                  uint32_t e_begin, uint32_t e_end, uint32_t Q, uint32_t tiles, uint32_t tile_vecs,
+                                  uint32_t pair_bytes) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp_in_block = threadIdx.x >> 5;
+  const uint64_t gwarp = (uint64_t)blockIdx.x * kPlanWarps + warp_in_block;
+  const uint32_t tile = (uint32_t)(gwarp % tiles);
+  const uint64_t q = gwarp / tiles;
+  const uint64_t e0_64 = e_begin + q * (uint64_t)Q;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+  uint2 *s_pair = reinterpret_cast<uint2 *>(smem_raw + 16);
+  // per-warp ring: STAGES barriers, then STAGES row buffers of tile_vecs float4
+  const uint32_t ring_bytes = 8u * STAGES + 8u * (STAGES & 1) + STAGES * tile_vecs * 16u;
+  unsigned char *ring = smem_raw + 16 + pair_bytes + (size_t)warp_in_block * ring_bytes;
+  uint64_t *sbar = reinterpret_cast<uint64_t *>(ring);
+  float4 *sbuf = reinterpret_cast<float4 *>(ring + 8u * STAGES + 8u * (STAGES & 1));
+  uint32_t cta_e_base = 0, bulk_bytes = 0;
+  {
+    const uint64_t cta_w0 = (uint64_t)blockIdx.x * kPlanWarps;
+    const uint64_t first_q = cta_w0 / tiles;
+    const uint64_t last_q = (cta_w0 + kPlanWarps - 1) / tiles;
+    uint64_t ce0 = e_begin + first_q * (uint64_t)Q;
+    uint64_t ce1 = e_begin + (last_q + 1) * (uint64_t)Q;
+    if (ce1 > e_end)
+      ce1 = e_end;
+    if (lane == 0)
+      for (int s = 0; s < STAGES; s++)
+        p_mbar_init(sbar + s, 1);
+    if (ce0 < ce1) {
+      cta_e_base = (uint32_t)(ce0 & ~1ull);
+      const uint32_t n_el = (uint32_t)(ce1 - cta_e_base);
+      bulk_bytes = (n_el * 8u) & ~15u;
+      if (threadIdx.x == 0) {
+        p_mbar_init(bar, 1);
+        if (n_el & 1u)
+          s_pair[n_el - 1] = __ldg(pairs + cta_e_base + n_el - 1);
+      }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0 && bulk_bytes) {
+      p_mbar_expect_tx(bar, bulk_bytes);
+      p_bulk_g2s(s_pair, pairs + cta_e_base, bulk_bytes, bar);
+    }
+  }
+  if (e0_64 >= e_end)
+    return;
+  const uint32_t e0 = (uint32_t)e0_64;
+  const uint32_t e1 = (e0_64 + Q < e_end) ? e0 + Q : e_end;
+  const uint32_t c0 = tile * tile_vecs + lane;
+  const uint32_t my_vecs = min(tile_vecs, ld4 - tile * tile_vecs); // float4 of this tile that exist in the row
+  const uint32_t row_bytes = my_vecs * 16u;
+  bool act[K];
+#pragma unroll
+  for (int k = 0; k < K; k++)
+    act[k] = (k * 32 + lane) < my_vecs;
+
+  uint32_t row = plan_find_row(off, n_rows, e0);
+  uint32_t row_end = __ldg(off + row + 1);
+  bool row_started_inside = __ldg(off + row) >= e0;
+  float4 acc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++)
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto flush = [&](bool whole) {
+    float *orow = out + (size_t)row * F;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint32_t col = (c0 + k * 32) * 4;
+      if (act[k] && col < F) {
+        if (whole)
+          flush_chunk<OUTV, false>(orow, col, F, acc[k]);
+        else
+          flush_chunk<OUTV, true>(orow, col, F, acc[k]);
+      }
+      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto advance = [&](uint32_t ee) {
+    flush(row_started_inside);
+    do {
+      row++;
+      row_end = __ldg(off + row + 1);
+    } while (ee >= row_end);
+    row_started_inside = true;
+  };
+  if (bulk_bytes)
+    p_mbar_wait(bar, 0);
+  const uint2 *sp = s_pair - cta_e_base;
+  auto issue = [&](uint32_t e, uint32_t stage) { // lane 0 only
+    const uint32_t src_row = sp[e].x;
+    p_mbar_expect_tx(sbar + stage, row_bytes);
+    p_bulk_g2s(sbuf + (size_t)stage * tile_vecs, in + (size_t)src_row * ld4 + tile * tile_vecs, row_bytes, sbar + stage);
+  };
+  if (lane == 0)
+    for (uint32_t s = 0; s < STAGES && e0 + s < e1; s++)
+      issue(e0 + s, s);
+  uint32_t stage = 0, parity = 0;
+  for (uint32_t e = e0; e < e1; e++) {
+    const float w = __uint_as_float(sp[e].y);
+    p_mbar_wait(sbar + stage, parity);
+    const float4 *b = sbuf + (size_t)stage * tile_vecs + lane;
+    float4 v[K];
+#pragma unroll
+    for (int k = 0; k < K; k++)
+      if (act[k])
+        v[k] = b[k * 32];
+    if (e >= row_end)
+      advance(e);
+#pragma unroll
+    for (int k = 0; k < K; k++)
+      if (act[k]) {
+        acc[k].x = fmaf(w, v[k].x, acc[k].x);
+        acc[k].y = fmaf(w, v[k].y, acc[k].y);
+        acc[k].z = fmaf(w, v[k].z, acc[k].z);
+        acc[k].w = fmaf(w, v[k].w, acc[k].w);
+      }
+    __syncwarp(); // every lane has consumed the stage (its values are in registers and used): it may be overwritten
+    if (lane == 0 && e + STAGES < e1)
+      issue(e + STAGES, stage);
+    if (++stage == STAGES) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  flush(row_started_inside && row_end <= e1);
+}
+
+template <int K, int STAGES, int OUTV, int MINB>
+static int launch_planned_tma(nts_gather_plan *pl, const PlanShape &sh, const float4 *in, uint32_t ld4, float *out,
+                              uint32_t F, uint32_t Q, cudaStream_t st);
+
 struct PlanShape {
-  int k, u, outv, minb;
+  int k, u, outv, minb, g;
   uint32_t tiles, tile_vecs;
 };
 
-template <int K, int U, int OUTV, int MINB>
+template <int K, int U, int OUTV, int MINB, int G = 1>
 static int launch_planned(nts_gather_plan *pl, const PlanShape &sh, const float4 *in, uint32_t ld4, float *out,
                           uint32_t F, uint32_t Q, cudaStream_t st) {
-  auto kern = planned_gather_sum_kernel<K, U, OUTV, MINB>;
-  const size_t smem = 16 + ((size_t)kPlanWarps * Q + 4) * 8;
+  auto kern = planned_gather_sum_kernel<K, U, OUTV, MINB, G>;
+  const size_t smem = 16 + ((size_t)kPlanWarps * G * Q + 4) * 8;
+  NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pl->last_launches = 0;
+  for (int s = 0; s < pl->slabs; s++) {
+    const uint64_t eb = pl->slab_edge[s], ee = pl->slab_edge[s + 1];
+    if (ee <= eb)
+      continue;
+    const uint64_t quanta = (ee - eb + Q - 1) / Q;
+    const uint64_t blocks = (quanta * sh.tiles + kPlanWarps * G - 1) / (kPlanWarps * G);
+    NTS_ARG_CHECK(blocks <= 0x7fffffffull, "aggregation grid too large");
+    kern<<<(unsigned)blocks, kPlanWarps * 32, smem, st>>>(in, ld4, out, F, pl->pairs, pl->voff + (size_t)s * pl->n_rows,
+                                                          pl->n_rows, (uint32_t)eb, (uint32_t)ee, Q, sh.tiles,
+                                                          sh.tile_vecs);
+    NTS_LAUNCH_CHECK();
+    pl->last_grid = (int)blocks;
+    pl->last_launches++;
+  }
+  return 0;
+}
+
+template <int K, int STAGES, int OUTV, int MINB>
+static int launch_planned_tma(nts_gather_plan *pl, const PlanShape &sh, const float4 *in, uint32_t ld4, float *out,
+                              uint32_t F, uint32_t Q, cudaStream_t st) {
+  auto kern = planned_gather_sum_tma_kernel<K, STAGES, OUTV, MINB>;
+  const uint32_t pair_bytes = (kPlanWarps * Q + 4) * 8;
+  const uint32_t ring_bytes = 8u * STAGES + 8u * (STAGES & 1) + STAGES * sh.tile_vecs * 16u;
+  const size_t smem = 16 + pair_bytes + (size_t)kPlanWarps * ring_bytes;
+  NTS_ARG_CHECK(smem <= 227 * 1024, "row-staging ring does not fit shared memory");
   NTS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pl->last_launches = 0;
   for (int s = 0; s < pl->slabs; s++) {
@@ -359,13 +536,31 @@ static int launch_planned(nts_gather_plan *pl, const PlanShape &sh, const float4
     NTS_ARG_CHECK(blocks <= 0x7fffffffull, "aggregation grid too large");
     kern<<<(unsigned)blocks, kPlanWarps * 32, smem, st>>>(in, ld4, out, F, pl->pairs, pl->voff + (size_t)s * pl->n_rows,
                                                           pl->n_rows, (uint32_t)eb, (uint32_t)ee, Q, sh.tiles,
-                                                          sh.tile_vecs);
+                                                          sh.tile_vecs, pair_bytes);
     NTS_LAUNCH_CHECK();
     pl->last_grid = (int)blocks;
     pl->last_launches++;
   }
   return 0;
 }
+
+#define NTS_PLAN_TMA_CASE(K_, S_, B_)                                                                               \
+  if (sh.k == K_ && stages == S_ && sh.minb == B_) {                                                                \
+    if (sh.outv == 4)                                                                                               \
+      return launch_planned_tma<K_, S_, 4, B_>(pl, sh, in4, ld4, out, F, Q, st);                                    \
+    if (sh.outv == 2)                                                                                               \
+      return launch_planned_tma<K_, S_, 2, B_>(pl, sh, in4, ld4, out, F, Q, st);                                    \
+    return launch_planned_tma<K_, S_, 1, B_>(pl, sh, in4, ld4, out, F, Q, st);                                      \
+  }
+
+#define NTS_PLAN_CASE_G(U_, B_, G_)                                                                                 \
+  if (sh.k == 1 && sh.u == U_ && sh.minb == B_ && sh.g == G_) {                                                     \
+    if (sh.outv == 4)                                                                                               \
+      return launch_planned<1, U_, 4, B_, G_>(pl, sh, in4, ld4, out, F, Q, st);                                     \
+    if (sh.outv == 2)                                                                                               \
+      return launch_planned<1, U_, 2, B_, G_>(pl, sh, in4, ld4, out, F, Q, st);                                     \
+    return launch_planned<1, U_, 1, B_, G_>(pl, sh, in4, ld4, out, F, Q, st);                                       \
+  }
 
 #define NTS_PLAN_CASE(K_, U_, B_)                                                                                   \
   if (sh.k == K_ && sh.u == U_ && sh.minb == B_) {                                                                  \
@@ -407,6 +602,9 @@ static int run_plan(nts_gather_plan *pl, const float *input, float *output, uint
   sh.k = (int)((sh.tile_vecs + 31) / 32);
   sh.tiles = (ld4 + sh.tile_vecs - 1) / sh.tile_vecs;
   sh.outv = (F % 4 == 0 && aligned_to(output, 16)) ? 4 : ((F % 2 == 0 && aligned_to(output, 8)) ? 2 : 1);
+  sh.g = ld4 <= 8 ? 4 : (ld4 <= 16 ? 2 : 1); // rows narrower than half / a quarter of a warp: virtual warps
+  if (g_plan_variant == 1 || getenv("NTS_PLAN_NO_SUBWARP"))
+    sh.g = 1;
   // (U, min CTAs/SM): U*K 16-byte loads in flight per lane
   // defaults = the largest U that compiles without spills at the occupancy point (ptxas -v); measured points for
   // the headline shapes in profiles/ (tools/k1_sweep.py)
@@ -426,17 +624,42 @@ static int run_plan(nts_gather_plan *pl, const float *input, float *output, uint
     if (g_plan_minb > 0)
       sh.minb = g_plan_minb;
   }
-  uint32_t Q = g_plan_q > 0 ? (uint32_t)g_plan_q : 512u;
+  uint32_t Q = g_plan_q > 0 ? (uint32_t)g_plan_q : 512u / sh.g; // the CTA's staged span stays 8 * 512 pairs
   if (g_plan_q <= 0) { // shrink for small inputs so every slab launch still fills the SMs
     const uint64_t per_slab = pl->n_edges / (uint64_t)pl->slabs + 1;
-    const uint64_t want_warps = (uint64_t)sm_count() * 64;
+    const uint64_t want_warps = (uint64_t)sm_count() * 64 * sh.g;
     while (Q > 32 && ((per_slab + Q - 1) / Q) * sh.tiles < want_warps)
       Q >>= 1;
   }
   Q = (Q + 31u) & ~31u;
+  if (Q * sh.g > 1024)
+    Q = (1024 / sh.g) & ~31u;
   pl->last_k = sh.k, pl->last_u = sh.u, pl->last_outv = sh.outv;
   const float4 *in4 = reinterpret_cast<const float4 *>(in);
   float *out = output;
+  if (g_plan_variant == 1) { // TMA row staging (measurement variant): U = ring depth
+    const int stages = sh.u >= 8 ? 8 : (sh.u >= 4 ? 4 : 2);
+    sh.minb = g_plan_minb > 0 ? g_plan_minb : (sh.k >= 4 ? 2 : 4);
+    NTS_PLAN_TMA_CASE(1, 8, 4)
+    NTS_PLAN_TMA_CASE(1, 4, 4)
+    NTS_PLAN_TMA_CASE(1, 8, 3)
+    NTS_PLAN_TMA_CASE(2, 4, 3)
+    NTS_PLAN_TMA_CASE(2, 4, 2)
+    NTS_PLAN_TMA_CASE(3, 4, 2)
+    NTS_PLAN_TMA_CASE(4, 4, 2)
+    NTS_PLAN_TMA_CASE(4, 2, 2)
+    NTS_PLAN_TMA_CASE(5, 4, 2)
+    NTS_PLAN_TMA_CASE(5, 2, 2)
+    NTS_PLAN_TMA_CASE(5, 4, 1)
+    NTS_PLAN_TMA_CASE(5, 8, 1)
+    return fail(-1, "no TMA row-staging instantiation for this (chunks, stages, occupancy) point", __FILE__, __LINE__);
+  }
+  NTS_PLAN_CASE_G(4, 4, 2)
+  NTS_PLAN_CASE_G(4, 4, 4)
+  NTS_PLAN_CASE_G(8, 3, 2)
+  NTS_PLAN_CASE_G(8, 3, 4)
+  if (sh.g != 1)
+    return fail(-1, "no virtual-warp instantiation for this (U, occupancy) point", __FILE__, __LINE__);
   NTS_PLAN_CASE(1, 8, 4)
   NTS_PLAN_CASE(1, 4, 4)
   NTS_PLAN_CASE(1, 8, 3)
@@ -667,6 +890,12 @@ int nts_gather_plan_last_launch(const nts_gather_plan *pl, int *launches, int *g
 int nts_gather_plan_run(nts_gather_plan *pl, const float *input, float *output, nts_vid_t feature_size, void *stream) {
   NTS_ARG_CHECK(pl != nullptr, "null plan");
   return run_plan(pl, input, output, feature_size, as_stream(stream));
+}
+
+int nts_gather_plan_set_variant(int variant) {
+  NTS_ARG_CHECK(variant == 0 || variant == 1, "variant must be 0 (register staging) or 1 (TMA row staging)");
+  g_plan_variant = variant;
+  return 0;
 }
 
 int nts_gather_plan_set_tuning(int u, int min_blocks, int edges_per_warp) {

@@ -173,7 +173,7 @@ class ExchangePlan:
 class GpuExchange:
     """Forward / backward drivers of the distributed fused aggregation on one GPU per rank."""
 
-    def __init__(self, pg, transport="nccl", group=None):
+    def __init__(self, pg, transport="nccl", group=None, n_buffers=None):
         if not torch.cuda.is_available():
             raise _lib.NtsError("GpuExchange needs a CUDA device (libnts_b200 has no CPU fallback)")
         self.pg = pg
@@ -186,7 +186,9 @@ class GpuExchange:
         self._staging = {}
         self._p2p = None
         if transport == "p2p" and self.P > 1:
-            self._p2p = _PeerWindows(self)
+            import os
+            nb = n_buffers if n_buffers else int(os.environ.get("NTS_EXCHANGE_BUFFERS", "2"))
+            self._p2p = _PeerWindows(self, n_buffers=nb)
         elif transport not in ("nccl", "p2p"):
             raise ValueError("transport must be 'nccl' or 'p2p'")
 

@@ -65,6 +65,22 @@ def set_kernel_timer(timer):
     _timer = timer
 
 
+class _timed:
+    """`with _timed(tag, F, edges, rows): launch` - CUDA events around the launch when a KernelTimer is installed."""
+
+    def __init__(self, tag, F, edges, rows):
+        self.ev = _timer.bracket(tag, F, edges, rows) if _timer else None
+
+    def __enter__(self):
+        if self.ev:
+            self.ev[0].record()
+
+    def __exit__(self, *exc):
+        if self.ev:
+            self.ev[1].record()
+        return False
+
+
 def segment_gather_sum(out, x, weight, indices, offsets, index_base, n_rows, n_edges):
     """out[r,:] += sum_e x[indices[e]-index_base,:] * weight[e]  (nts_segment_gather_sum)."""
     _lib.call("nts_segment_gather_sum", _ptr(x), _ptr(out), _ptr(weight), _ptr(indices), _ptr(offsets),
@@ -449,12 +465,14 @@ class DistGPUFusedGATOp(_EdgeOp):
         seg_max = torch.empty((pg.owned_vertices, H), dtype=torch.float32, device=x.device)
         seg_sum = torch.empty_like(seg_max)
         slots = self.slot_indices(pg)
-        _lib.call("nts_gat_softmax_stats", _ptr(seg_max), _ptr(seg_sum), _ptr(s), _ptr(d), _ptr(slots),
-                  _ptr(pg.column_offset_gpu), 0, pg.owned_vertices, H, self.slope, _stream())
+        with _timed("gat_stats", x.shape[1], pg.owned_edges, pg.owned_vertices):
+            _lib.call("nts_gat_softmax_stats", _ptr(seg_max), _ptr(seg_sum), _ptr(s), _ptr(d), _ptr(slots),
+                      _ptr(pg.column_offset_gpu), 0, pg.owned_vertices, H, self.slope, _stream())
         out = torch.zeros((pg.owned_vertices, x.shape[1]), dtype=torch.float32, device=x.device)
-        _lib.call("nts_gat_fused_aggregate_forward", _ptr(x), _ptr(out), _ptr(s), _ptr(d), _ptr(seg_max),
-                  _ptr(seg_sum), _ptr(slots), _ptr(pg.column_offset_gpu), 0,
-                  pg.owned_vertices, pg.owned_edges, x.shape[1], H, self.slope, _stream())
+        with _timed("gat_fwd", x.shape[1], pg.owned_edges, pg.owned_vertices):
+            _lib.call("nts_gat_fused_aggregate_forward", _ptr(x), _ptr(out), _ptr(s), _ptr(d), _ptr(seg_max),
+                      _ptr(seg_sum), _ptr(slots), _ptr(pg.column_offset_gpu), 0,
+                      pg.owned_vertices, pg.owned_edges, x.shape[1], H, self.slope, _stream())
         self._saved = (x, s, d, seg_max, seg_sum, out)
         return out
 
@@ -473,11 +491,12 @@ class DistGPUFusedGATOp(_EdgeOp):
             # no per-edge atomics: a destination-major and a source-major pass, each with register accumulators
             slot_off, slot_dst = self.slot_csr(pg)
             pack = torch.empty((pg.owned_vertices, H, 4), dtype=torch.float32, device=x.device)
-            _lib.call("nts_gat_fused_aggregate_backward_two_pass", _ptr(dm), _ptr(ds), _ptr(dd), _ptr(pack), _ptr(x),
-                      _ptr(s), _ptr(d), _ptr(seg_max), _ptr(seg_sum), _ptr(out_dot_g), _ptr(g),
-                      _ptr(self.slot_indices(pg)), _ptr(pg.column_offset_gpu), 0,
-                      _ptr(slot_off), _ptr(slot_dst), pg.owned_vertices, x.shape[0], x.shape[1], H, self.slope,
-                      _stream())
+            with _timed("gat_bwd", x.shape[1], 2 * pg.owned_edges, pg.owned_vertices):
+                _lib.call("nts_gat_fused_aggregate_backward_two_pass", _ptr(dm), _ptr(ds), _ptr(dd), _ptr(pack),
+                          _ptr(x), _ptr(s), _ptr(d), _ptr(seg_max), _ptr(seg_sum), _ptr(out_dot_g), _ptr(g),
+                          _ptr(self.slot_indices(pg)), _ptr(pg.column_offset_gpu), 0,
+                          _ptr(slot_off), _ptr(slot_dst), pg.owned_vertices, x.shape[0], x.shape[1], H, self.slope,
+                          _stream())
             return dm, ds, dd
         _lib.call("nts_gat_fused_aggregate_backward", _ptr(dm), _ptr(ds), _ptr(dd), _ptr(x), _ptr(s), _ptr(d),
                   _ptr(seg_max), _ptr(seg_sum), _ptr(out_dot_g), _ptr(g), _ptr(pg.row_indices_gpu),

@@ -12,6 +12,8 @@ WORKLOADS = {
     # name: (V, E_random, layers)            SURVEY.md 8 preamble / 8d
     "reddit": (232965, 114615892, [602, 128, 41]),
     "products": (2449029, 61859140, [100, 128, 47]),
+    "papers100m": (111059956, 1615685872, [128, 128, 172]),   # config E: generated per partition (zipf_edges_owned)
+    "papers_eighth": (13882494, 201960734, [128, 128, 172]),  # one GPU's share of config E as a stand-alone graph
     "cora_sized": (2708, 10858, [1433, 128, 7]),
     "tiny": (20000, 400000, [602, 128, 41]),
 }
@@ -20,24 +22,64 @@ SEED_GRAPH = 0x5EED0001
 SEED_FEATURES = 0x5EED0002
 
 
-def zipf_edges(V, E, device, s=1.0, seed=SEED_GRAPH, self_loops=True, chunk=1 << 26):
-    """int64 (src, dst) on `device`; deterministic for a given (V, E, s, seed) and GPU architecture."""
+def _zipf_stream(V, E, device, s, seed, chunk):
+    """Yields (src, dst) int64 chunks of the E random edges; the sequence is a function of (V, E, s, seed, chunk) and
+    the GPU architecture only, so every rank - and the one-shot and the streaming consumers - see the same graph."""
     gen = torch.Generator(device=device).manual_seed(seed)
     w = torch.arange(1, V + 1, device=device, dtype=torch.float64).pow_(-s)
     cdf = torch.cumsum(w / w.sum(), 0)
+    del w
     perm_s = torch.randperm(V, generator=gen, device=device)
     perm_d = torch.randperm(V, generator=gen, device=device)
-    src_parts, dst_parts = [], []
     done = 0
     while done < E:
         n = min(chunk, E - done)
         u = torch.rand(n, generator=gen, device=device, dtype=torch.float64)
-        src_parts.append(perm_s[torch.searchsorted(cdf, u).clamp_(max=V - 1)])
+        src = perm_s[torch.searchsorted(cdf, u).clamp_(max=V - 1)]
         u = torch.rand(n, generator=gen, device=device, dtype=torch.float64)
-        dst_parts.append(perm_d[torch.searchsorted(cdf, u).clamp_(max=V - 1)])
+        dst = perm_d[torch.searchsorted(cdf, u).clamp_(max=V - 1)]
+        del u
+        yield src, dst
         done += n
+
+
+def zipf_edges(V, E, device, s=1.0, seed=SEED_GRAPH, self_loops=True, chunk=1 << 26):
+    """int64 (src, dst) on `device`; deterministic for a given (V, E, s, seed) and GPU architecture."""
+    src_parts, dst_parts = [], []
+    for src, dst in _zipf_stream(V, E, device, s, seed, chunk):
+        src_parts.append(src)
+        dst_parts.append(dst)
     if self_loops:
         loops = torch.arange(V, device=device, dtype=torch.int64)
+        src_parts.append(loops)
+        dst_parts.append(loops)
+    return torch.cat(src_parts), torch.cat(dst_parts)
+
+
+def zipf_degrees(V, E, device, s=1.0, seed=SEED_GRAPH, self_loops=True, chunk=1 << 26):
+    """(out_degree, in_degree) int64 [V] of the same graph WITHOUT materialising its edge list (pass 1 of the
+    streaming generation of graphs that do not fit one GPU next to their features: papers100M-shaped)."""
+    out_d = torch.zeros(V, dtype=torch.int64, device=device)
+    in_d = torch.zeros(V, dtype=torch.int64, device=device)
+    for src, dst in _zipf_stream(V, E, device, s, seed, chunk):
+        out_d += torch.bincount(src, minlength=V)
+        in_d += torch.bincount(dst, minlength=V)
+    if self_loops:
+        out_d += 1
+        in_d += 1
+    return out_d, in_d
+
+
+def zipf_edges_owned(V, E, device, v0, v1, s=1.0, seed=SEED_GRAPH, self_loops=True, chunk=1 << 26):
+    """The edges of the same graph whose DESTINATION lies in [v0, v1) (pass 2: what rank p of a partitioned run
+    keeps), in stream order, self loops of the owned vertices last."""
+    src_parts, dst_parts = [], []
+    for src, dst in _zipf_stream(V, E, device, s, seed, chunk):
+        keep = (dst >= v0) & (dst < v1)
+        src_parts.append(src[keep])
+        dst_parts.append(dst[keep])
+    if self_loops:
+        loops = torch.arange(v0, v1, device=device, dtype=torch.int64)
         src_parts.append(loops)
         dst_parts.append(loops)
     return torch.cat(src_parts), torch.cat(dst_parts)

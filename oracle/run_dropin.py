@@ -43,6 +43,14 @@ DROP_RATE:0.0
 """
 
 
+def _visible_devices(rank, n_gpus):
+    """The reference never calls cudaSetDevice (always device 0, core/NtsScheduler.hpp:299), so rank r gets physical
+    GPU r % n_gpus AS its device 0 - but every other GPU stays visible behind it: CUDA IPC can only map a peer's
+    window if the exporting device is visible to the importing process."""
+    first = rank % n_gpus
+    return ",".join(str((first + k) % n_gpus) for k in range(n_gpus))
+
+
 def _run_ranks(binary, cfg, nprocs, env, timeout):
     """rank 0's output and the first non-zero exit status of `nprocs` ranks under the MPI stand-in
     (oracle/shim/mpi.h: NTS_SHIM_SIZE / NTS_SHIM_RANK / NTS_SHIM_DIR).  The reference never calls cudaSetDevice
@@ -63,7 +71,7 @@ def _run_ranks(binary, cfg, nprocs, env, timeout):
     try:
         for r in range(nprocs):
             e = dict(env, NTS_SHIM_SIZE=str(nprocs), NTS_SHIM_RANK=str(r), NTS_SHIM_DIR=scratch,
-                     CUDA_VISIBLE_DEVICES=str(r % n_gpus))
+                     CUDA_VISIBLE_DEVICES=_visible_devices(r, n_gpus))
             procs.append(subprocess.Popen([binary, cfg], env=e, text=True,
                                           stdout=subprocess.PIPE if r == 0 else subprocess.DEVNULL,
                                           stderr=subprocess.STDOUT if r == 0 else subprocess.DEVNULL))
@@ -123,7 +131,7 @@ DROP_RATE:0.0
 """
 
 
-def run_synthetic(binary, algo, V, layers, edge_file, epochs, timeout=1500):
+def run_synthetic(binary, algo, V, layers, edge_file, epochs, timeout=1500, nprocs=1):
     """Per-epoch seconds of a reference toolkit on a synthetic edge file: from its own `Times[...(s)]` print when the
     toolkit has one (GCN_EAGER_single.hpp:250-252), else from the arrival times of its per-epoch loss lines."""
     import time
@@ -134,6 +142,20 @@ def run_synthetic(binary, algo, V, layers, edge_file, epochs, timeout=1500):
         env.setdefault("NTS_THREADS", str(os.cpu_count()))
         env["OMP_NUM_THREADS"] = env["NTS_THREADS"]
         t0 = time.perf_counter()
+        others, scratch = [], None
+        if nprocs > 1:   # ranks 1.. in the background, rank 0 is the one we read
+            import shutil
+            import torch
+            n_gpus = max(1, torch.cuda.device_count())
+            scratch = tempfile.mkdtemp(prefix="nts_shim_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            env = dict(env, NTS_SHIM_SIZE=str(nprocs), NTS_SHIM_DIR=scratch,
+                       NTS_THREADS=str(max(1, int(env["NTS_THREADS"]) // nprocs)))
+            env["OMP_NUM_THREADS"] = env["NTS_THREADS"]
+            for r in range(1, nprocs):
+                others.append(subprocess.Popen([binary, cfg], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                                               env=dict(env, NTS_SHIM_RANK=str(r),
+                                                        CUDA_VISIBLE_DEVICES=_visible_devices(r, n_gpus))))
+            env = dict(env, NTS_SHIM_RANK="0", CUDA_VISIBLE_DEVICES=_visible_devices(0, n_gpus))
         p = subprocess.Popen([binary, cfg], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
         stamps, own = [], []
         for line in p.stdout:
@@ -144,12 +166,41 @@ def run_synthetic(binary, algo, V, layers, edge_file, epochs, timeout=1500):
                     own.append(float(m.group(1)))
         p.wait(timeout=timeout)
         total = time.perf_counter() - t0
+        for q in others:
+            try:
+                q.wait(timeout=120)
+            except subprocess.TimeoutExpired:
+                q.kill()
+        if scratch:
+            import shutil
+            shutil.rmtree(scratch, ignore_errors=True)
     if own:
         per = own[1:] if len(own) > 1 else own
     else:
         per = [b - a for a, b in zip(stamps[:-1], stamps[1:])]
-    return {"algo": algo, "rc": p.returncode, "epochs_seen": len(stamps), "s_per_epoch_after_first": per,
+    return {"algo": algo, "ranks": nprocs, "rc": p.returncode, "epochs_seen": len(stamps), "s_per_epoch_after_first": per,
             "s_per_epoch_median": sorted(per)[len(per) // 2] if per else None, "wall_s_incl_load": total}
+
+
+def synthetic_dist_main(div, epochs, nprocs):
+    """The reference's own host code (toolkits/main.cpp + toolkits/GCN.hpp, unchanged) at P ranks, ONE GPU PER RANK,
+    with the drop-in ForwardGPUfuseOp on the peer-memory exchange (nts_dropin_dist_main), on 1/div of the
+    Reddit-shaped graph.  Every rank loads the edge file through the MPI stand-in like the reference does."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.dirname(HERE))
+    from neutronstarlite_b200 import synth
+    V, E_rand, layers = synth.WORKLOADS["reddit"]
+    src, dst = synth.zipf_edges(V, E_rand // div, torch.device("cpu"))
+    with tempfile.TemporaryDirectory() as d:
+        efile = os.path.join(d, "syn.edge")
+        torch.stack([src, dst], 1).numpy().astype(np.uint32).tofile(efile)
+        res = {"graph": "reddit-shaped 1/%d: %d V, %d E, LAYERS %s" % (div, V, int(src.numel()), "-".join(map(str, layers))),
+               "gpus": torch.cuda.device_count(), "ranks": nprocs}
+        res["dropin_dist_GCN"] = run_synthetic(os.path.join(REF, "nts_dropin_dist_main"), "GCN", V,
+                                               "-".join(map(str, layers)), efile, epochs, nprocs=nprocs)
+    print(json.dumps(res, indent=1))
+    return 0
 
 
 def synthetic_main(div, epochs):
@@ -188,6 +239,8 @@ def main():
                     help="compare ours vs the reference's own kernels through the reference's host code on 1/DIV of "
                          "the Reddit-shaped graph")
     a = ap.parse_args()
+    if a.synthetic and a.dist_exchange:
+        return synthetic_dist_main(a.synthetic, min(a.epochs, 8), a.np)
     if a.synthetic:
         return synthetic_main(a.synthetic, min(a.epochs, 6))
     res = {}

@@ -74,6 +74,25 @@ def test_plan_matches_oracle(F, slabs):
     assert np.array_equal(cnt[:, 0], np.diff(off.astype(np.int64)).astype(np.float32))
 
 
+@pytest.mark.parametrize("F", [602, 128, 41, 1433])
+def test_plan_tma_row_staging_variant_matches_oracle(F):
+    """Variant 1 (feature rows staged in shared memory by per-row cp.async.bulk, the north star's TMA staging): same
+    results as the oracle; kept for measurement, the default stays variant 0."""
+    from neutronstarlite_b200 import _lib
+    rng = np.random.default_rng(2000 + F)
+    n_rows, n_src, n_edges = 500, 700, 30000
+    off, idx, w = make_graph(rng, n_rows, n_src, n_edges)
+    X = rng.uniform(-1, 1, (n_src, F)).astype(np.float32)
+    ref = oracle_c.segment_gather_sum(off, idx, w, X)
+    _lib.call("nts_gather_plan_set_variant", 1)
+    try:
+        for slabs in (1, 4):
+            _, got = run_plan(off, idx, w, X, 0, slabs, n_src)
+            row_close(got, ref)
+    finally:
+        _lib.call("nts_gather_plan_set_variant", 0)
+
+
 def test_plan_slot_table_and_unaligned_views():
     """Indices through a slot table (the receive-staging slots of the exchange) and a feature matrix whose rows are
     16-byte multiples but whose base pointer is only 4-byte aligned (a view): the padded workspace must kick in."""

@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--workload", default="reddit")
+    ap.add_argument("--tma", action="store_true", help="also time variant 1 (TMA row staging)")
+    ap.add_argument("--slabs", default=None, help="comma list of slab counts to try (default: 1, auto, 2, 4, 8, 16, 24)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     L = _lib.load()
@@ -72,7 +74,11 @@ def main():
             call(c, ref, x)
             emit({"zipf": zipf, "dir": direction, "F": F, "kernel": "plain", "ms": med, "ms_best": best})
             auto = int(L.nts_gather_plan_pick_slabs(V, c.edge_size, V, F, 0))
+            c.__dict__.pop("_gather_plan_for", None)
             slab_list = sorted(set([1, auto] + ([] if args.quick else [2, 4, 8, 16, 24])))
+            if args.slabs:
+                slab_list = sorted(set(int(v) for v in args.slabs.split(",")))
+                auto = slab_list[-1]
             for S in slab_list:
                 ops.set_plan_mode("on", S)
                 pts = [(0, 0)]
@@ -94,6 +100,25 @@ def main():
                     emit({"zipf": zipf, "dir": direction, "F": F, "kernel": "plan", "slabs": S, "u": u, "minb": b,
                           "ms": med, "ms_best": best, "max_row_rel_diff_vs_plain": err})
                 _lib.call("nts_gather_plan_set_tuning", 0, 0, 0)
+                if args.tma and S in (1, auto):   # variant 1: rows staged in shared memory by per-row TMA copies
+                    _lib.call("nts_gather_plan_set_variant", 1)
+                    for (u, b) in ([(2, 2), (4, 2), (4, 1), (8, 1)] if F > 512 else [(4, 4), (8, 4), (8, 3)]):
+                        _lib.call("nts_gather_plan_set_tuning", u, b, 0)
+                        try:
+                            med, best = timed(lambda: call(c, y, x))
+                            chk = torch.zeros_like(y)
+                            call(c, chk, x)
+                            torch.cuda.synchronize()
+                            err = float(((chk - ref).abs().max(dim=1).values /
+                                         ref.abs().max(dim=1).values.clamp(min=1e-30)).max().item())
+                            emit({"zipf": zipf, "dir": direction, "F": F, "kernel": "plan_tma_rows", "slabs": S,
+                                  "stages": u, "minb": b, "ms": med, "ms_best": best,
+                                  "max_row_rel_diff_vs_plain": err})
+                        except Exception as exc:
+                            emit({"zipf": zipf, "dir": direction, "F": F, "kernel": "plan_tma_rows", "slabs": S,
+                                  "stages": u, "minb": b, "error": str(exc)[:80]})
+                    _lib.call("nts_gather_plan_set_variant", 0)
+                    _lib.call("nts_gather_plan_set_tuning", 0, 0, 0)
                 c.__dict__.pop("_gather_plans", None)   # free this slab count's arrays before the next
                 torch.cuda.empty_cache()
             ops.set_plan_mode("auto")
