@@ -338,6 +338,10 @@ typedef struct nts_exchange_desc {
   const nts_vid_t *send_rows_all;           /* device: concatenation over j != rank (ascending) of those local row ids */
   const nts_vid_t *fwd_push_offset;         /* [P] first row of MY rows inside rank j's receive staging */
   const nts_vid_t *bwd_push_offset;         /* [P] first row of MY partials inside rank i's gradient staging */
+  /* rows of MY partition that are sources of my own in-edges (active sources of the local chunk, ascending); only
+   * the mirror fetch below needs them */
+  const nts_vid_t *local_need;              /* device */
+  nts_vid_t local_need_count;
 } nts_exchange_desc;
 
 nts_exchange *nts_exchange_create(const nts_exchange_desc *desc);
@@ -359,6 +363,13 @@ int nts_exchange_open_peers(nts_exchange *ex, const unsigned char *window_handle
 int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t feature_size, void *stream);
 /* dX_p += sum_j A_{j<-p}^T dY_j (ForwardGPUfuseOp::backward, :75-90); dx zeroed by caller */
 int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t feature_size, void *stream);
+/* DistGPUGetDepNbrOp (core/ntsDistGPUGraphOp.hpp:48-143) on the same windows - the reference moves the whole feature
+ * matrix GPU -> host -> MPI -> host -> GPU.  forward: mirror[MirrorIndex[s], :] = X[s, :] for every source s of a local
+ * in-edge ([owned_mirrors, F], partition order); backward: dx[v, :] += every partition's mirror gradient of my vertex
+ * v (dx zeroed by the caller). */
+int nts_exchange_fetch_mirrors(nts_exchange *ex, const float *x, float *mirror, nts_vid_t feature_size, void *stream);
+int nts_exchange_return_mirror_grads(nts_exchange *ex, const float *mirror_grad, float *dx, nts_vid_t feature_size,
+                                     void *stream);
 
 /* ---- exchange plan builder (host C++): the reference's chunks -> the arrays of nts_exchange_desc ------------------------
  * C++ twin of neutronstarlite_b200/exchange.py::ExchangePlan for hosts without Python (the reference's own host

@@ -115,6 +115,7 @@ class ExchangeDesc(C.Structure):
         ("chunks", C.POINTER(ExchangeChunk)),
         ("need_count", C.POINTER(_u32)), ("send_count", C.POINTER(_u32)),
         ("send_rows_all", _vp), ("fwd_push_offset", C.POINTER(_u32)), ("bwd_push_offset", C.POINTER(_u32)),
+        ("local_need", _vp), ("local_need_count", _u32),
     ]
 
 
@@ -137,6 +138,8 @@ SIGNATURES.update({
     "nts_exchange_open_peers": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "nts_exchange_forward": (_int, [_vp, _vp, _vp, _u32, _vp]),
     "nts_exchange_backward": (_int, [_vp, _vp, _vp, _u32, _vp]),
+    "nts_exchange_fetch_mirrors": (_int, [_vp, _vp, _vp, _u32, _vp]),
+    "nts_exchange_return_mirror_grads": (_int, [_vp, _vp, _vp, _u32, _vp]),
 })
 
 

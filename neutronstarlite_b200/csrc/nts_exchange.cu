@@ -587,6 +587,116 @@ static int backward_impl(nts_exchange *ex, const float *g, float *dx, nts_vid_t 
   return 0;
 }
 
+// mirror[M, F] = the feature row of every source of a local in-edge, in MirrorIndex order (partition 0's active rows,
+// partition 1's, ...; core/PartitionedGraph.hpp:295-305): remote rows arrive through the same push as the forward
+// exchange, the own partition's rows by a local gather.
+static int fetch_impl(nts_exchange *ex, const float *x, float *mirror, nts_vid_t F, void *stream) {
+  const nts_exchange_desc &d = ex->d;
+  cudaStream_t st = as_stream(stream);
+  const int P = ex->P, p = ex->p;
+  const uint32_t own = d.local_need_count;
+  NTS_ARG_CHECK(own == 0 || d.local_need, "exchange descriptor lacks local_need (rows of this partition it reads itself)");
+  if (P == 1)
+    return own ? nts_gather_rows(mirror, x, d.local_need, own, F, stream) : 0;
+  NTS_TRY(ready_for(ex, F));
+  const uint32_t epoch = ++ex->epoch;
+  const size_t buf = (size_t)(epoch % ex->n_buffers) * ex->buf_floats;
+  PushArgs a;
+  a.n = 0;
+  a.epoch = epoch;
+  a.wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
+  for (int s = 1; s < P; s++) {
+    const int j = (p - s + P) % P;
+    PushTarget &t = a.t[a.n++];
+    t.rows = d.send_rows_all + ex->srecv_offs[j];
+    t.n_rows = ex->send_count[j];
+    t.src_row0 = 0;
+    t.dst = ex->peer_window[j] + buf + (size_t)ex->fwd_push_off[j] * F;
+    t.pushed_flag = ex->peer_flags[j] + p;
+    t.consumed_flag = ex->flags + P + j;
+  }
+  NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st));
+  NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
+  NTS_TRY(launch_push(ex, a, x, F, ex->comm));
+  const size_t before = ex->recv_offs[p]; // staged rows of the partitions before mine
+  if (own)
+    NTS_TRY(nts_gather_rows(mirror + before * F, x, d.local_need, own, F, st));
+  uint32_t mask = 0;
+  for (int j = 0; j < P; j++)
+    if (j != p)
+      mask |= 1u << j;
+  wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, mask, epoch, ex->timeout_ns, ex->err_dev);
+  NTS_LAUNCH_CHECK();
+  if (before)
+    NTS_CUDA_OK(cudaMemcpyAsync(mirror, ex->window + buf, before * F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (ex->recv_total > before)
+    NTS_CUDA_OK(cudaMemcpyAsync(mirror + (before + own) * F, ex->window + buf + before * F,
+                                (ex->recv_total - before) * (size_t)F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  signal_consumed_kernel<<<1, 32, 0, st>>>(ex->d_peer_flags, P, p, epoch);
+  NTS_LAUNCH_CHECK();
+  NTS_CUDA_OK(cudaEventRecord(ex->ev_comm, ex->comm));
+  NTS_CUDA_OK(cudaStreamWaitEvent(st, ex->ev_comm, 0));
+  return 0;
+}
+
+// dx[v, :] += the mirror gradients every partition holds for my vertex v (dx zeroed by the caller): slices of
+// mirror_grad go straight from the caller's buffer into the owners' windows.
+static int return_impl(nts_exchange *ex, const float *gm, float *dx, nts_vid_t F, void *stream) {
+  const nts_exchange_desc &d = ex->d;
+  cudaStream_t st = as_stream(stream);
+  const int P = ex->P, p = ex->p;
+  const uint32_t own = d.local_need_count;
+  NTS_ARG_CHECK(own == 0 || d.local_need, "exchange descriptor lacks local_need");
+  if (P == 1)
+    return own ? nts_scatter_add_rows(dx, gm, d.local_need, own, F, stream) : 0;
+  NTS_TRY(ready_for(ex, F));
+  const uint32_t epoch = ++ex->epoch;
+  const size_t buf = (size_t)(epoch % ex->n_buffers) * ex->buf_floats;
+  const size_t before = ex->recv_offs[p];
+  PushArgs a;
+  a.n = 0;
+  a.epoch = epoch;
+  a.wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
+  for (int s = 1; s < P; s++) {
+    const int i = (p + s) % P;
+    PushTarget &t = a.t[a.n++];
+    t.rows = nullptr;
+    t.n_rows = ex->need_count[i];
+    t.src_row0 = ex->recv_offs[i] + (i > p ? own : 0u); // partition i's block of the mirror matrix
+    t.dst = ex->peer_window[i] + buf + (size_t)ex->bwd_push_off[i] * F;
+    t.pushed_flag = ex->peer_flags[i] + p;
+    t.consumed_flag = ex->flags + P + i;
+  }
+  NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st));
+  NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
+  NTS_TRY(launch_push(ex, a, gm, F, ex->comm));
+  if (own)
+    NTS_TRY(nts_scatter_add_rows(dx, gm + before * F, d.local_need, own, F, st));
+  uint32_t mask = 0;
+  for (int j = 0; j < P; j++)
+    if (j != p)
+      mask |= 1u << j;
+  wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, mask, epoch, ex->timeout_ns, ex->err_dev);
+  NTS_LAUNCH_CHECK();
+  if (ex->send_total)
+    NTS_TRY(nts_scatter_add_rows_atomic(dx, ex->window + buf, d.send_rows_all, ex->send_total, F, st));
+  signal_consumed_kernel<<<1, 32, 0, st>>>(ex->d_peer_flags, P, p, epoch);
+  NTS_LAUNCH_CHECK();
+  NTS_CUDA_OK(cudaEventRecord(ex->ev_comm, ex->comm));
+  NTS_CUDA_OK(cudaStreamWaitEvent(st, ex->ev_comm, 0));
+  return 0;
+}
+
+int nts_exchange_fetch_mirrors(nts_exchange *ex, const float *x, float *mirror, nts_vid_t F, void *stream) {
+  NTS_ARG_CHECK(ex && (x || ex->d.owned_vertices == 0) && mirror, "null argument");
+  return check_wait_error(ex, fetch_impl(ex, x, mirror, F, stream));
+}
+
+int nts_exchange_return_mirror_grads(nts_exchange *ex, const float *mirror_grad, float *dx, nts_vid_t F, void *stream) {
+  NTS_ARG_CHECK(ex && mirror_grad && (dx || ex->d.owned_vertices == 0), "null argument");
+  return check_wait_error(ex, return_impl(ex, mirror_grad, dx, F, stream));
+}
+
 // Y_p += sum_i A_{p<-i} X_i.  `y` must be zeroed by the caller (accumulate semantics, like every aggregation entry).
 int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t F, void *stream) {
   NTS_ARG_CHECK(ex != nullptr, "null engine");

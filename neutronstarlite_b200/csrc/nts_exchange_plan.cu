@@ -363,6 +363,11 @@ nts_exchange *nts_exchange_create_from_plan(nts_exchange_plan *pl, const nts_dev
   }
   if (rc)
     return nullptr;
+  pl->need_dev.assign(P, nullptr);
+  if (upload(pl, pl->need[p], &pl->need_dev[p]))
+    return nullptr;
+  d.local_need = pl->need_dev[p];
+  d.local_need_count = (nts_vid_t)pl->need[p].size();
   d.chunks = pl->dev_chunks.data();
   d.need_count = pl->need_count.data();
   d.send_count = pl->send_count.data();

@@ -277,6 +277,10 @@ class GpuExchange:
         cur = torch.cuda.current_stream()
         M = sum(plan.need_count)
         mirror = torch.zeros((M, F), dtype=torch.float32, device=x.device)
+        if self._p2p is not None:   # the peer-memory engine: rows pushed into the receive windows, no NCCL
+            self._p2p.reserve(F)
+            _lib.call("nts_exchange_fetch_mirrors", self._p2p.handle, _ptr(x), _ptr(mirror), F, cur.cuda_stream)
+            return mirror
         if P == 1:
             if M:
                 _lib.call("nts_gather_rows", _ptr(mirror), _ptr(x), _ptr(plan.need[0]), M, F, cur.cuda_stream)
@@ -301,6 +305,11 @@ class GpuExchange:
         F = gm.shape[1]
         cur = torch.cuda.current_stream()
         dx = torch.zeros((pg.owned_vertices, F), dtype=torch.float32, device=gm.device)
+        if self._p2p is not None:
+            self._p2p.reserve(F)
+            _lib.call("nts_exchange_return_mirror_grads", self._p2p.handle, _ptr(gm.contiguous()), _ptr(dx), F,
+                      cur.cuda_stream)
+            return dx
         if P == 1:
             if gm.shape[0]:
                 _lib.call("nts_scatter_add_rows", _ptr(dx), _ptr(gm), _ptr(plan.need[0]), gm.shape[0], F,
@@ -415,6 +424,7 @@ class _PeerWindows:
         d.send_rows_all = _ptr(plan.send_rows_all)
         d.fwd_push_offset = self._keep["fwd_off"]
         d.bwd_push_offset = self._keep["bwd_off"]
+        d.local_need, d.local_need_count = _ptr(plan.need[p]), plan.need_count[p]
         self.handle = L.nts_exchange_create(C.byref(d))
         if not self.handle:
             raise _lib.NtsError("nts_exchange_create failed: " + L.nts_last_error().decode())

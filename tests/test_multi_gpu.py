@@ -133,6 +133,15 @@ def _shared_gpu_worker(rank, world, port, case, plan_all, q):
             torch.cuda.synchronize()
             np.testing.assert_allclose(y.cpu().numpy(), ref_y, rtol=1e-4, atol=1e-5)
             np.testing.assert_allclose(dx.cpu().numpy(), ref_dx, rtol=1e-4, atol=2e-5)
+        # mirror fetch / return (DistGPUGetDepNbrOp) on the same windows, against the reference's DistGetDepNbrOp
+        dep = ops.DistGPUGetDepNbrOp(pg, None, exchange=ex)
+        mirror = dep.forward(x)
+        torch.cuda.synchronize()
+        assert np.array_equal(mirror.cpu().numpy(), z["r%d/dep_mirror" % rank].reshape(-1, F))
+        gm = torch.from_numpy(z["r%d/dep_Gm" % rank].reshape(-1, F)).to(dev)
+        dxm = dep.backward(gm)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dxm.cpu().numpy(), z["r%d/dep_dX" % rank].reshape(-1, F), rtol=1e-4, atol=2e-5)
         # a wider matrix through the same engine: the window is re-reserved (release -> barrier -> reallocate)
         F2 = 602
         gen = torch.Generator().manual_seed(3)
