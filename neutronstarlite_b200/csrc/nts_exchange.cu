@@ -132,7 +132,7 @@ __global__ void signal_consumed_kernel(uint32_t *const *peer_flags, int P, int p
 
 // The persistent push kernel: all CTAs work through the targets in order; a target's flag is raised by the last CTA
 // to finish its share of that target's rows.  VEC floats per lane access (rows are F floats, F % VEC == 0, both
-// sides VEC*4-byte aligned); 4 independent loads in flight per lane.
+// sides VEC*4-byte aligned); 4-8 independent loads in flight per lane (four rows per warp step).
 template <int VEC>
 __global__ void __launch_bounds__(256)
     push_rows_kernel(const PushArgs a, const float *__restrict__ src, uint32_t F, uint32_t *tickets,
@@ -149,17 +149,43 @@ __global__ void __launch_bounds__(256)
       if (a.wait_epoch && threadIdx.x == 0)
         bounded_wait_geq(t.consumed_flag, a.wait_epoch, timeout_ns, err, 2, k);
       __syncthreads();
-      for (uint32_t r = gwarp; r < t.n_rows; r += n_warps) {
-        const uint32_t srow = t.rows ? __ldg(t.rows + r) : t.src_row0 + r;
-        const V *s = reinterpret_cast<const V *>(src + (size_t)srow * F);
-        V *d = reinterpret_cast<V *>(t.dst + (size_t)r * F);
-        uint32_t c = lane;
-        for (; c + 96 < nvec; c += 128) {
-          V v0 = __ldg(s + c), v1 = __ldg(s + c + 32), v2 = __ldg(s + c + 64), v3 = __ldg(s + c + 96);
-          d[c] = v0, d[c + 32] = v1, d[c + 64] = v2, d[c + 96] = v3;
+      // four rows per warp step: 4 (narrow rows) or 8 independent loads per lane are in flight before the first store
+      for (uint32_t r0 = gwarp * 4; r0 < t.n_rows; r0 += n_warps * 4) {
+        const V *s[4];
+        V *d[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t r = min(r0 + k, t.n_rows - 1);
+          const uint32_t srow = t.rows ? __ldg(t.rows + r) : t.src_row0 + r;
+          s[k] = reinterpret_cast<const V *>(src + (size_t)srow * F);
+          d[k] = reinterpret_cast<V *>(t.dst + (size_t)r * F);
         }
-        for (; c < nvec; c += 32)
-          d[c] = __ldg(s + c);
+        const uint32_t live = min(4u, t.n_rows - r0);
+        uint32_t c = lane;
+        for (; c + 32 < nvec; c += 64) {
+          V v[4][2];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            v[k][0] = __ldg(s[k] + c);
+            v[k][1] = __ldg(s[k] + c + 32);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((uint32_t)k < live) {
+              d[k][c] = v[k][0];
+              d[k][c + 32] = v[k][1];
+            }
+        }
+        if (c < nvec) {
+          V v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            v[k] = __ldg(s[k] + c);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if ((uint32_t)k < live)
+              d[k][c] = v[k];
+        }
       }
       __threadfence_system(); // my stores to the peer are ordered before the ticket below
     }
@@ -327,7 +353,7 @@ nts_exchange *nts_exchange_create(const nts_exchange_desc *desc) {
   }
   if (const char *t = getenv("NTS_EXCHANGE_PLAN_MIN_EDGES"))
     ex->plan_min_edges = strtoull(t, nullptr, 10);
-  ex->push_ctas = std::max(8, sm_count() / 3); // enough memory-level parallelism for NVLink, a third of the SMs at most
+  ex->push_ctas = std::max(8, sm_count() / 2); // enough memory-level parallelism for NVLink, half of the SMs at most
   if (const char *t = getenv("NTS_EXCHANGE_PUSH_CTAS")) {
     const int n = atoi(t);
     if (n > 0)

@@ -43,7 +43,9 @@ class ExchangePlan:
     """Setup-time index structures (per PartitionedGraph).  Backend-agnostic: built with torch ops on whatever
     device the chunk arrays live on and torch.distributed collectives (works with gloo on CPU tensors)."""
 
-    def __init__(self, pg, group=None):
+    def __init__(self, pg, group=None, merged=True):
+        """merged = also build the one-launch CSC / compact CSR over ALL remote chunks (what the NCCL transport
+        aggregates from); the peer-memory engine works per chunk and skips it."""
         self.pg = pg
         self.P = pg.partitions
         self.p = pg.partition_id
@@ -91,7 +93,14 @@ class ExchangePlan:
             self.send_rows = [None]
         self.recv_total = sum(self.need_count[i] for i in range(P) if i != p)
         self.send_total = sum(self.send_count[j] for j in range(P) if j != p)
-        self._merge_remote()
+        rows = [self.send_rows[j] for j in range(P) if j != p and self.send_rows[j] is not None]
+        self.send_rows_all = torch.cat(rows).contiguous() if rows else torch.zeros(0, dtype=torch.int32, device=dev)
+        self.remote_edges = sum(int(chunks[i].edge_size) for i in range(P) if i != p)
+        self.remote_col_offset = self.remote_slots = self.remote_w = None
+        self.bwd_offsets = self.bwd_indices = self.bwd_w = None
+        self.recv_offs = np.concatenate([[0], np.cumsum([self.need_count[i] if i != p else 0 for i in range(P)])])
+        if merged:
+            self._merge_remote()
 
     def _merge_remote(self):
         """One CSC over ALL remote chunks (sources = slots of the single receive staging buffer) and one compact CSR
@@ -179,7 +188,7 @@ class GpuExchange:
         self.pg = pg
         self.P, self.p = pg.partitions, pg.partition_id
         self.group = group
-        self.plan = ExchangePlan(pg, group)
+        self.plan = ExchangePlan(pg, group, merged=(transport != "p2p"))
         self.transport = transport
         self.device = self.plan.device
         self.comm_stream = torch.cuda.Stream(device=self.device)
