@@ -140,3 +140,23 @@ def test_host_builder_equals_the_pinned_oracle_on_random_graphs():
                 assert np.array_equal(c.source_active, rc.source_active)
             mi, n_mirrors = O.mirror_index(edges, V, po, r)
             assert np.array_equal(pg.MirrorIndex, mi) and pg.owned_mirrors == n_mirrors
+
+
+def test_streaming_generator_matches_one_shot_generator():
+    """Config E is generated per partition in two streaming passes (synth.zipf_degrees / zipf_edges_owned): same
+    graph as the one-shot generator - degrees exactly, owned edge multiset exactly - for every rank of a 3-way split."""
+    import torch
+    from neutronstarlite_b200 import synth
+    d = torch.device("cpu")
+    V, E = 6000, 150000
+    s, t = synth.zipf_edges(V, E, d, chunk=1 << 15)
+    od, idg = synth.zipf_degrees(V, E, d, chunk=1 << 15)
+    assert torch.equal(od, torch.bincount(s, minlength=V)) and torch.equal(idg, torch.bincount(t, minlength=V))
+    cuts = [0, 1024, 4096, V]
+    seen = 0
+    for r in range(3):
+        so, to = synth.zipf_edges_owned(V, E, d, cuts[r], cuts[r + 1], chunk=1 << 15)
+        keep = (t >= cuts[r]) & (t < cuts[r + 1])
+        assert torch.equal((to * V + so).sort().values, (t[keep] * V + s[keep]).sort().values)
+        seen += int(so.numel())
+    assert seen == int(s.numel())

@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: tools/gpurun_retry.sh <gpurun args...>   - retries while the pod answers "busy" (exit 3: nothing charged)
-for attempt in $(seq 1 12); do
+for attempt in $(seq 1 60); do
   /usr/local/graft/bin/gpurun "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi

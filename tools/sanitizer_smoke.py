@@ -27,6 +27,26 @@ for variant in (1, 2):
         y = op.forward(x)
         dx = op.backward(y)
 _lib.call("nts_aggregate_set_variant", 0, 0)
+# preprocessed aggregation (nts_gather_plan): slab counts, both staging variants, virtual warps (F <= 64), padded rows
+c = pg.graph_chunks[0]
+for variant in (0, 1):
+    _lib.call("nts_gather_plan_set_variant", variant)
+    for slabs in (1, 3):
+        ops.set_plan_mode("on", slabs)
+        for F in (602, 128, 64, 41, 7):
+            x = torch.rand((V, F), device=dev)
+            ops.gather_by_dst_from_src(c, torch.zeros_like(x), x)
+            ops.gather_by_src_from_dst(c, torch.zeros_like(x), x)
+        c.__dict__.pop("_gather_plans", None)
+_lib.call("nts_gather_plan_set_variant", 0)
+ops.set_plan_mode("on", 0)                      # measured slab count (nts_gather_plan_create_tuned)
+x = torch.rand((V, 128), device=dev)
+ops.gather_by_dst_from_src(c, torch.zeros_like(x), x)
+ops.set_plan_mode("auto")
+# fused Adam
+W, M, Vv, G = (torch.rand(1000, device=dev) for _ in range(4))
+_lib.call("nts_adam_update", W.data_ptr(), M.data_ptr(), Vv.data_ptr(), G.data_ptr(), 1000, 1e-4, 0.9, 0.999, 0.01, 1e-9,
+          torch.cuda.current_stream().cuda_stream)
 ex = GpuExchange(pg)
 dep = ops.DistGPUGetDepNbrOp(pg, None, exchange=ex)
 for H, D in ((1, 16), (4, 8)):
