@@ -506,6 +506,7 @@ def main():
             ref_gpu = {"error": repr(exc)}
     # ---- N > 1: parity of the distributed operator on THIS box, outside the timed regions
     parity = multi_gpu_parity(pg, op_kwargs["exchange"], feats.detach(), layers, rank, world, dev) if world > 1 else None
+    timeline = exchange_timeline(op_kwargs["exchange"], feats.detach(), layers, world, dev) if world > 1 else None
     agg_ms = sum(d["ms"] for d in ksum.values()) / args.steps   # this rank's aggregation launches per step
     agg_only = {"ms_per_step": agg_ms, "edges_per_s": agg_calls * E_total / (agg_ms * 1e-3) if agg_ms > 0 else None,
                 "note": "CUDA-event time of the aggregation launches only (rank 0), SURVEY 8d"}
@@ -535,7 +536,7 @@ def main():
                     "tape_note": "like the reference (core/ntsContext.hpp:283) the first graph op gets no backward "
                                  "aggregation; unlike it, the dead input-layer dY = dH W^T GEMM is skipped too "
                                  "(<2% of the epoch)"},
-            "parity": parity,
+            "parity": parity, "exchange_timeline": timeline,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "kernels": kernels, "aggregation_only": agg_only, "reference_gpu_kernels": ref_gpu, "clocks": clocks,
         }
@@ -602,6 +603,46 @@ def multi_gpu_parity(pg, ex, feats, layers, rank, world, dev):
             "reference": "float64 torch index_add on the reference-layout chunk arrays, %d columns, all %d ranks" % (C, world),
             "max_row_rel_forward": fwd, "max_row_rel_backward": bwd, "max_rel": max(fwd, bwd), "tolerance": 1e-4,
             "ok": bool(max(fwd, bwd) <= 1e-4)}
+
+
+def exchange_timeline(ex, feats, layers, world, dev):
+    """Per-phase device time of ONE forward exchange per width on the engine (outside the timed regions): push kernel
+    (side stream), local chunk, and per ring step the wait for the rows of partition (p+s) and the aggregation of
+    chunk (p+s).  Rank 0's numbers plus the max over ranks of the whole call and of the summed waits."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from neutronstarlite_b200 import _lib, ops
+    if getattr(ex, "_p2p", None) is None:
+        return None
+    L = _lib.load()
+    h = ex._p2p.handle
+    op = ops.ForwardGPUfuseOp(ex.pg, None, exchange=ex)
+    out = {}
+    n = 2 * world + 1
+    buf = (C.c_float * n)()
+    _lib.call("nts_exchange_set_trace", h, 1)
+    try:
+        for F in sorted(set(layers[:-1]), reverse=True):
+            x = feats if F == feats.shape[1] else torch.rand((feats.shape[0], F), device=dev)
+            op.forward(x.contiguous())          # warm (plans exist from the timed epochs)
+            dist.barrier()
+            op.forward(x.contiguous())
+            _lib.call("nts_exchange_last_timeline", h, buf, n)
+            ms = [float(v) for v in buf]
+            waits = sum(ms[2 * s] for s in range(1, world))
+            worst = torch.tensor([ms[2 * world], waits, ms[0]], dtype=torch.float64, device=dev)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            out["F%d" % F] = {"rank0_ms": {"push_kernel": ms[0], "local_chunk": ms[1],
+                                           "wait_for_partition": [ms[2 * s] for s in range(1, world)],
+                                           "aggregate_chunk": [ms[2 * s + 1] for s in range(1, world)],
+                                           "whole_call": ms[2 * world]},
+                            "max_over_ranks_ms": {"whole_call": float(worst[0].item()),
+                                                  "sum_of_waits": float(worst[1].item()),
+                                                  "push_kernel": float(worst[2].item())}}
+    finally:
+        _lib.call("nts_exchange_set_trace", h, 0)
+    return out
 
 
 def reference_gpu_kernels(pg, feats, layers, torch):

@@ -363,6 +363,11 @@ int nts_exchange_open_peers(nts_exchange *ex, const unsigned char *window_handle
 int nts_exchange_forward(nts_exchange *ex, const float *x, float *y, nts_vid_t feature_size, void *stream);
 /* dX_p += sum_j A_{j<-p}^T dY_j (ForwardGPUfuseOp::backward, :75-90); dx zeroed by caller */
 int nts_exchange_backward(nts_exchange *ex, const float *g, float *dx, nts_vid_t feature_size, void *stream);
+/* per-phase device timeline of the last forward (measurement): [0] push kernel, [1] local chunk, then per ring step
+ * s: [2s] wait for the rows of partition (p+s), [2s+1] aggregation of chunk (p+s); [2P] whole call.  2P+1 floats (ms);
+ * nts_exchange_last_timeline synchronises the device */
+int nts_exchange_set_trace(nts_exchange *ex, int enable);
+int nts_exchange_last_timeline(nts_exchange *ex, float *ms, int capacity);
 /* DistGPUGetDepNbrOp (core/ntsDistGPUGraphOp.hpp:48-143) on the same windows - the reference moves the whole feature
  * matrix GPU -> host -> MPI -> host -> GPU.  forward: mirror[MirrorIndex[s], :] = X[s, :] for every source s of a local
  * in-edge ([owned_mirrors, F], partition order); backward: dx[v, :] += every partition's mirror gradient of my vertex

@@ -138,6 +138,8 @@ SIGNATURES.update({
     "nts_exchange_open_peers": (_int, [_vp, C.c_char_p, C.c_char_p]),
     "nts_exchange_forward": (_int, [_vp, _vp, _vp, _u32, _vp]),
     "nts_exchange_backward": (_int, [_vp, _vp, _vp, _u32, _vp]),
+    "nts_exchange_set_trace": (_int, [_vp, _int]),
+    "nts_exchange_last_timeline": (_int, [_vp, C.POINTER(C.c_float), _int]),
     "nts_exchange_fetch_mirrors": (_int, [_vp, _vp, _vp, _u32, _vp]),
     "nts_exchange_return_mirror_grads": (_int, [_vp, _vp, _vp, _u32, _vp]),
 })

@@ -73,6 +73,10 @@ struct nts_exchange {
   uint64_t plan_min_edges = 1u << 20;
   unsigned long long timeout_ns = 30ull * 1000000000ull;
   int push_ctas = 0;
+  // optional per-phase timeline of the last forward (nts_exchange_set_trace): events on both streams
+  bool trace = false;
+  std::vector<cudaEvent_t> tev; // [0] call start, [1] push begin, [2] push end, [3] local chunk done,
+                                // then per ring step s: [4+2(s-1)] rows of (p+s) have landed, [5+2(s-1)] chunk aggregated
 };
 
 namespace nts {
@@ -434,6 +438,9 @@ int nts_exchange_destroy(nts_exchange *ex) {
   for (cudaEvent_t e : ex->ev_peer)
     if (e)
       cudaEventDestroy(e);
+  for (cudaEvent_t e : ex->tev)
+    if (e)
+      cudaEventDestroy(e);
   delete ex;
   return 0;
 }
@@ -538,17 +545,30 @@ static int forward_impl(nts_exchange *ex, const float *x, float *y, nts_vid_t F,
     t.pushed_flag = ex->peer_flags[j] + p;
     t.consumed_flag = ex->flags + P + j;
   }
+  const bool tr = ex->trace && (int)ex->tev.size() >= 4 + 2 * (P - 1);
   NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st)); // x is ready
+  if (tr)
+    NTS_CUDA_OK(cudaEventRecord(ex->tev[0], st));
   NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
+  if (tr)
+    NTS_CUDA_OK(cudaEventRecord(ex->tev[1], ex->comm));
   NTS_TRY(launch_push(ex, a, x, F, ex->comm));
+  if (tr)
+    NTS_CUDA_OK(cudaEventRecord(ex->tev[2], ex->comm));
   // ---- main stream: local chunk, then the remote chunks as their rows arrive
   NTS_TRY(aggregate_chunk(ex, p, true, x, y, F, st));
+  if (tr)
+    NTS_CUDA_OK(cudaEventRecord(ex->tev[3], st));
   for (int s = 1; s < P; s++) {
     const int i = (p + s) % P;
     wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, 1u << i, epoch, ex->timeout_ns, ex->err_dev);
     NTS_LAUNCH_CHECK();
+    if (tr)
+      NTS_CUDA_OK(cudaEventRecord(ex->tev[4 + 2 * (s - 1)], st));
     if (ex->need_count[i])
       NTS_TRY(aggregate_chunk(ex, i, true, ex->window + buf + (size_t)ex->recv_offs[i] * F, y, F, st));
+    if (tr)
+      NTS_CUDA_OK(cudaEventRecord(ex->tev[5 + 2 * (s - 1)], st));
   }
   signal_consumed_kernel<<<1, 32, 0, st>>>(ex->d_peer_flags, P, p, epoch);
   NTS_LAUNCH_CHECK();
@@ -710,6 +730,38 @@ static int return_impl(nts_exchange *ex, const float *gm, float *dx, nts_vid_t F
   NTS_LAUNCH_CHECK();
   NTS_CUDA_OK(cudaEventRecord(ex->ev_comm, ex->comm));
   NTS_CUDA_OK(cudaStreamWaitEvent(st, ex->ev_comm, 0));
+  return 0;
+}
+
+// Per-phase device timeline of forward calls (evidence for profiles/): enable, run ONE forward, read.
+int nts_exchange_set_trace(nts_exchange *ex, int enable) {
+  NTS_ARG_CHECK(ex != nullptr, "null engine");
+  if (enable && ex->tev.empty()) {
+    ex->tev.assign(4 + 2 * (ex->P > 1 ? ex->P - 1 : 0), nullptr);
+    for (cudaEvent_t &e : ex->tev)
+      NTS_CUDA_OK(cudaEventCreate(&e));
+  }
+  ex->trace = enable != 0;
+  return 0;
+}
+
+// ms[0] push kernel (side stream), ms[1] local chunk, then per ring step s = 1..P-1: ms[2s] time the main stream sat
+// waiting for the rows of partition (p+s) after it was ready for them, ms[2s+1] aggregation of chunk (p+s);
+// ms[2P] whole call on the main stream (2P+1 entries).  Synchronises the device.
+int nts_exchange_last_timeline(nts_exchange *ex, float *ms, int capacity) {
+  NTS_ARG_CHECK(ex && ms && ex->trace && !ex->tev.empty(), "tracing is not enabled");
+  const int P = ex->P, n = 2 * P + 1;
+  NTS_ARG_CHECK(capacity >= n, "timeline buffer too small (2P+1 floats)");
+  NTS_CUDA_OK(cudaDeviceSynchronize());
+  NTS_CUDA_OK(cudaEventElapsedTime(&ms[0], ex->tev[1], ex->tev[2]));
+  NTS_CUDA_OK(cudaEventElapsedTime(&ms[1], ex->tev[0], ex->tev[3]));
+  cudaEvent_t prev = ex->tev[3];
+  for (int s = 1; s < P; s++) {
+    NTS_CUDA_OK(cudaEventElapsedTime(&ms[2 * s], prev, ex->tev[4 + 2 * (s - 1)]));
+    NTS_CUDA_OK(cudaEventElapsedTime(&ms[2 * s + 1], ex->tev[4 + 2 * (s - 1)], ex->tev[5 + 2 * (s - 1)]));
+    prev = ex->tev[5 + 2 * (s - 1)];
+  }
+  NTS_CUDA_OK(cudaEventElapsedTime(&ms[2 * P], ex->tev[0], prev));
   return 0;
 }
 
