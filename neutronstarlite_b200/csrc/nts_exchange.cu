@@ -766,12 +766,16 @@ int nts_exchange_last_timeline(nts_exchange *ex, float *ms, int capacity) {
 }
 
 int nts_exchange_fetch_mirrors(nts_exchange *ex, const float *x, float *mirror, nts_vid_t F, void *stream) {
-  NTS_ARG_CHECK(ex && (x || ex->d.owned_vertices == 0) && mirror, "null argument");
+  // (a rank without in-edges has an empty mirror matrix: NULL is fine then, it still takes part in the protocol)
+  NTS_ARG_CHECK(ex && (x || ex->d.owned_vertices == 0) && (mirror || ex->recv_total + ex->d.local_need_count == 0),
+                "null argument");
   return check_wait_error(ex, fetch_impl(ex, x, mirror, F, stream));
 }
 
 int nts_exchange_return_mirror_grads(nts_exchange *ex, const float *mirror_grad, float *dx, nts_vid_t F, void *stream) {
-  NTS_ARG_CHECK(ex && mirror_grad && (dx || ex->d.owned_vertices == 0), "null argument");
+  NTS_ARG_CHECK(ex && (mirror_grad || ex->recv_total + ex->d.local_need_count == 0) &&
+                    (dx || ex->d.owned_vertices == 0),
+                "null argument");
   return check_wait_error(ex, return_impl(ex, mirror_grad, dx, F, stream));
 }
 

@@ -18,7 +18,9 @@ if [ "$N" -le 4 ]; then
 fi
 run bench_r2_reddit --steps 20 --warmup 5
 run bench_r2_products --workload products --steps 20 --warmup 5
-run bench_r2_reddit_nccl --steps 10 --warmup 3 --transport nccl --no-e2e
+if [ "$N" -le 2 ]; then
+  run bench_r2_reddit_nccl --steps 10 --warmup 3 --transport nccl --no-e2e
+fi
 if [ "$N" -ge 8 ]; then
   NTS_EXCHANGE_BUFFERS=1 run bench_r2_papers100m --workload papers100m --steps 5 --warmup 3 --no-e2e
 fi

@@ -22,6 +22,9 @@ WANT = [
     "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__inst_executed.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__warps_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "sm__inst_executed_pipe_lsu.sum",
 ]
 
 
@@ -57,11 +60,19 @@ def main():
                 return 0.0
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(v["unit"], 1)
             return v["value"] * scale
-        wide = [k for k in kernels if "<2, 5" in k["kernel"]]
-        if wide:
-            t = sum(gb(k, "dram__bytes_read.sum") + gb(k, "dram__bytes_write.sum") for k in wide) / len(wide)
-            json.dump({"dram_bytes_per_launch_fwd_F602": t, "source": os.path.basename(rep)},
-                      open(os.path.join(os.path.dirname(out), "traffic.json"), "w"))
+        # round 2: the dominant kernel is planned_gather_sum_kernel<5, ...> (F=602: five float4 chunks per lane);
+        # one aggregation CALL is one launch per slab plus the row-padding copy, summed here per call
+        wide = [k for k in kernels if "planned_gather_sum_kernel<5" in k["kernel"]]
+        narrow = [k for k in kernels if "planned_gather_sum_kernel<1" in k["kernel"]]
+        res = {}
+        for tag, ks in (("fwd_F602", wide), ("F128", narrow)):
+            if ks:
+                t = sum(gb(k, "dram__bytes_read.sum") + gb(k, "dram__bytes_write.sum") for k in ks) / len(ks)
+                res[tag] = {"bytes": t, "kernel": ks[0]["kernel"], "launches_averaged": len(ks),
+                            "source": os.path.basename(rep) + " (ncu --set full, per launch; the bench's measured "
+                                      "slab count is 1 on this graph, so one launch per call)"}
+        if res:
+            json.dump(res, open(os.path.join(os.path.dirname(out), "traffic.json"), "w"), indent=1)
     print("wrote", out + ".json", len(kernels), "kernels")
 
 
