@@ -50,6 +50,7 @@ struct nts_exchange {
   nts_exchange_desc d;
   std::vector<nts_exchange_chunk> chunks;
   std::vector<uint32_t> need_count, send_count, recv_offs, srecv_offs, fwd_push_off, bwd_push_off;
+  std::vector<char> send_all;         // [P] peer j reads ALL my rows in order: its forward push is one contiguous copy
   uint32_t recv_total = 0, send_total = 0;
   // exported receive window + flags
   float *window = nullptr;
@@ -123,6 +124,17 @@ __global__ void wait_pushed_kernel(const uint32_t *flags, uint32_t mask, uint32_
   const int i = threadIdx.x;
   if (i < kMaxPeers && ((mask >> i) & 1u))
     bounded_wait_geq(flags + i, epoch, timeout_ns, err, 1, i);
+}
+
+// contiguous slices travel by the copy engines (cudaMemcpyAsync into the peer's window, no SM time): a one-thread wait
+// before and a one-thread flag store after the copy, in stream order
+__global__ void wait_consumed_kernel(const uint32_t *flag, uint32_t epoch, unsigned long long timeout_ns, int *err,
+                                     int index) {
+  bounded_wait_geq(flag, epoch, timeout_ns, err, 2, index);
+}
+__global__ void signal_pushed_kernel(uint32_t *peer_flag, uint32_t epoch) {
+  __threadfence_system();
+  st_release_sys(peer_flag, epoch);
 }
 
 // consumed[p] = epoch in every peer's flags
@@ -263,6 +275,54 @@ static int launch_push(nts_exchange *ex, const PushArgs &a, const float *src, ui
   return 0;
 }
 
+// One contiguous slice into peer j's window through the copy engines: [wait until j has consumed the buffer] -> peer
+// copy -> raise pushed[p] at j.  n_rows == 0 still raises the flag (every rank signals every peer every call).
+static int dma_push(nts_exchange *ex, int j, const float *src, size_t dst_row, uint32_t n_rows, uint32_t F, size_t buf,
+                    uint32_t epoch, uint32_t wait_epoch, cudaStream_t st) {
+  if (n_rows) {
+    if (wait_epoch) {
+      wait_consumed_kernel<<<1, 1, 0, st>>>(ex->flags + ex->P + j, wait_epoch, ex->timeout_ns, ex->err_dev, j);
+      NTS_LAUNCH_CHECK();
+    }
+    NTS_CUDA_OK(cudaMemcpyAsync(ex->peer_window[j] + buf + dst_row * F, src, (size_t)n_rows * F * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+  }
+  signal_pushed_kernel<<<1, 1, 0, st>>>(ex->peer_flags[j] + ex->p, epoch);
+  NTS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Forward-style push of my rows to every peer in ring order p-1, p-2, ...: peers that read ALL my rows get one
+// copy-engine transfer each, the others share persistent gather kernels (consecutive ones batched into one launch).
+static int push_my_rows(nts_exchange *ex, const float *x, uint32_t F, size_t buf, uint32_t epoch, uint32_t wait_epoch) {
+  const int P = ex->P, p = ex->p;
+  PushArgs a;
+  a.n = 0;
+  a.epoch = epoch;
+  a.wait_epoch = wait_epoch;
+  for (int s = 1; s < P; s++) {
+    const int j = (p - s + P) % P;
+    if (ex->send_all[j]) {
+      if (a.n) {
+        NTS_TRY(launch_push(ex, a, x, F, ex->comm));
+        a.n = 0;
+      }
+      NTS_TRY(dma_push(ex, j, x, ex->fwd_push_off[j], ex->send_count[j], F, buf, epoch, wait_epoch, ex->comm));
+      continue;
+    }
+    PushTarget &t = a.t[a.n++];
+    t.rows = ex->d.send_rows_all + ex->srecv_offs[j];
+    t.n_rows = ex->send_count[j];
+    t.src_row0 = 0;
+    t.dst = ex->peer_window[j] + buf + (size_t)ex->fwd_push_off[j] * F;
+    t.pushed_flag = ex->peer_flags[j] + p;
+    t.consumed_flag = ex->flags + P + j;
+  }
+  if (a.n)
+    NTS_TRY(launch_push(ex, a, x, F, ex->comm));
+  return 0;
+}
+
 // aggregation of one chunk direction: preprocessed plan for big chunks, the plain kernel otherwise
 static int aggregate_chunk(nts_exchange *ex, int i, bool forward, const float *in, float *out, uint32_t F,
                            cudaStream_t st) {
@@ -346,6 +406,20 @@ nts_exchange *nts_exchange_create(const nts_exchange_desc *desc) {
   }
   ex->recv_total = ex->recv_offs[P];
   ex->send_total = ex->srecv_offs[P];
+  ex->send_all.assign(P, 0);
+  if (P > 1 && ex->send_total && desc->send_rows_all && !getenv("NTS_EXCHANGE_NO_DMA")) {
+    std::vector<uint32_t> rows(ex->send_total);
+    if (cudaMemcpy(rows.data(), desc->send_rows_all, rows.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) == cudaSuccess)
+      for (int j = 0; j < P; j++) {
+        if (j == p || ex->send_count[j] != desc->owned_vertices || !desc->owned_vertices)
+          continue;
+        bool ident = true;
+        const uint32_t *r = rows.data() + ex->srecv_offs[j];
+        for (uint32_t k = 0; k < ex->send_count[j] && ident; k++)
+          ident = r[k] == k;
+        ex->send_all[j] = ident;
+      }
+  }
   ex->peer_window.assign(P, nullptr);
   ex->peer_flags.assign(P, nullptr);
   ex->plan_fwd.resize(P), ex->plan_bwd.resize(P);
@@ -530,21 +604,7 @@ static int forward_impl(nts_exchange *ex, const float *x, float *y, nts_vid_t F,
   NTS_TRY(ready_for(ex, F));
   const uint32_t epoch = ++ex->epoch;
   const size_t buf = (size_t)(epoch % ex->n_buffers) * ex->buf_floats;
-  // ---- side stream: push my rows to every peer, ring order p-1, p-2, ... (the peer that needs them first)
-  PushArgs a;
-  a.n = 0;
-  a.epoch = epoch;
-  a.wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
-  for (int s = 1; s < P; s++) {
-    const int j = (p - s + P) % P;
-    PushTarget &t = a.t[a.n++];
-    t.rows = d.send_rows_all + ex->srecv_offs[j];
-    t.n_rows = ex->send_count[j];
-    t.src_row0 = 0;
-    t.dst = ex->peer_window[j] + buf + (size_t)ex->fwd_push_off[j] * F;
-    t.pushed_flag = ex->peer_flags[j] + p;
-    t.consumed_flag = ex->flags + P + j;
-  }
+  const uint32_t wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
   const bool tr = ex->trace && (int)ex->tev.size() >= 4 + 2 * (P - 1);
   NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st)); // x is ready
   if (tr)
@@ -552,7 +612,8 @@ static int forward_impl(nts_exchange *ex, const float *x, float *y, nts_vid_t F,
   NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
   if (tr)
     NTS_CUDA_OK(cudaEventRecord(ex->tev[1], ex->comm));
-  NTS_TRY(launch_push(ex, a, x, F, ex->comm));
+  // ---- side stream: my rows to every peer, ring order p-1, p-2, ... (the peer that needs them first)
+  NTS_TRY(push_my_rows(ex, x, F, buf, epoch, wait_epoch));
   if (tr)
     NTS_CUDA_OK(cudaEventRecord(ex->tev[2], ex->comm));
   // ---- main stream: local chunk, then the remote chunks as their rows arrive
@@ -602,18 +663,8 @@ static int backward_impl(nts_exchange *ex, const float *g, float *dx, nts_vid_t 
       NTS_TRY(aggregate_chunk(ex, i, false, g, slice, F, st));
     NTS_CUDA_OK(cudaEventRecord(ex->ev_peer[i], st));
     NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_peer[i], 0));
-    PushArgs a;
-    a.n = 1;
-    a.epoch = epoch;
-    a.wait_epoch = wait_epoch;
-    PushTarget &t = a.t[0];
-    t.rows = nullptr;
-    t.n_rows = ex->need_count[i];
-    t.src_row0 = ex->recv_offs[i];
-    t.dst = ex->peer_window[i] + buf + (size_t)ex->bwd_push_off[i] * F;
-    t.pushed_flag = ex->peer_flags[i] + p;
-    t.consumed_flag = ex->flags + P + i;
-    NTS_TRY(launch_push(ex, a, ex->bsend, F, ex->comm));
+    NTS_TRY(dma_push(ex, i, ex->bsend + (size_t)ex->recv_offs[i] * F, ex->bwd_push_off[i], ex->need_count[i], F, buf,
+                     epoch, wait_epoch, ex->comm));
   }
   // ---- local chunk overlaps with the pushes; then everything the peers computed for my rows
   NTS_TRY(aggregate_chunk(ex, p, false, g, dx, F, st));
@@ -647,23 +698,10 @@ static int fetch_impl(nts_exchange *ex, const float *x, float *mirror, nts_vid_t
   NTS_TRY(ready_for(ex, F));
   const uint32_t epoch = ++ex->epoch;
   const size_t buf = (size_t)(epoch % ex->n_buffers) * ex->buf_floats;
-  PushArgs a;
-  a.n = 0;
-  a.epoch = epoch;
-  a.wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
-  for (int s = 1; s < P; s++) {
-    const int j = (p - s + P) % P;
-    PushTarget &t = a.t[a.n++];
-    t.rows = d.send_rows_all + ex->srecv_offs[j];
-    t.n_rows = ex->send_count[j];
-    t.src_row0 = 0;
-    t.dst = ex->peer_window[j] + buf + (size_t)ex->fwd_push_off[j] * F;
-    t.pushed_flag = ex->peer_flags[j] + p;
-    t.consumed_flag = ex->flags + P + j;
-  }
+  const uint32_t wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
   NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st));
   NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
-  NTS_TRY(launch_push(ex, a, x, F, ex->comm));
+  NTS_TRY(push_my_rows(ex, x, F, buf, epoch, wait_epoch));
   const size_t before = ex->recv_offs[p]; // staged rows of the partitions before mine
   if (own)
     NTS_TRY(nts_gather_rows(mirror + before * F, x, d.local_need, own, F, st));
@@ -699,23 +737,14 @@ static int return_impl(nts_exchange *ex, const float *gm, float *dx, nts_vid_t F
   const uint32_t epoch = ++ex->epoch;
   const size_t buf = (size_t)(epoch % ex->n_buffers) * ex->buf_floats;
   const size_t before = ex->recv_offs[p];
-  PushArgs a;
-  a.n = 0;
-  a.epoch = epoch;
-  a.wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
-  for (int s = 1; s < P; s++) {
-    const int i = (p + s) % P;
-    PushTarget &t = a.t[a.n++];
-    t.rows = nullptr;
-    t.n_rows = ex->need_count[i];
-    t.src_row0 = ex->recv_offs[i] + (i > p ? own : 0u); // partition i's block of the mirror matrix
-    t.dst = ex->peer_window[i] + buf + (size_t)ex->bwd_push_off[i] * F;
-    t.pushed_flag = ex->peer_flags[i] + p;
-    t.consumed_flag = ex->flags + P + i;
-  }
+  const uint32_t wait_epoch = epoch > (uint32_t)ex->n_buffers ? epoch - ex->n_buffers : 0u;
   NTS_CUDA_OK(cudaEventRecord(ex->ev_main, st));
   NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_main, 0));
-  NTS_TRY(launch_push(ex, a, gm, F, ex->comm));
+  for (int s = 1; s < P; s++) {
+    const int i = (p + s) % P; // partition i's block of the mirror-gradient matrix goes to its owner
+    NTS_TRY(dma_push(ex, i, gm + (size_t)(ex->recv_offs[i] + (i > p ? own : 0u)) * F, ex->bwd_push_off[i],
+                     ex->need_count[i], F, buf, epoch, wait_epoch, ex->comm));
+  }
   if (own)
     NTS_TRY(nts_scatter_add_rows(dx, gm + before * F, d.local_need, own, F, st));
   uint32_t mask = 0;
