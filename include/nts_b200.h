@@ -125,6 +125,19 @@ nts_gather_plan *nts_gather_plan_create_tuned(const nts_vid_t *offsets, const nt
                                               const nts_vid_t *slot_of, nts_vid_t index_base, nts_vid_t n_rows,
                                               uint64_t n_edges, nts_vid_t gather_rows, nts_vid_t feature_size,
                                               void *stream);
+/* Several chunks merged into ONE plan: part-local output row r becomes row_add + r, a mapped index g becomes index_add
+ * + g; inside a (slab, row) segment the parts follow each other in the order given.  n_slabs = 0 measures the slab
+ * count for feature_size.  Used by the exchange engine to aggregate all remote chunks of a rank in one launch. */
+typedef struct nts_plan_part {
+  const nts_vid_t *offsets, *indices;   /* [n_rows+1], [n_edges] of this part */
+  const float *weight;                  /* [n_edges] or NULL */
+  const nts_vid_t *slot_of;             /* optional slot table applied to the indices */
+  nts_vid_t index_base, index_add, n_rows, row_add;
+  uint64_t n_edges;
+} nts_plan_part;
+nts_gather_plan *nts_gather_plan_create_parts(const nts_plan_part *parts, int n_parts, nts_vid_t n_rows,
+                                              nts_vid_t gather_rows, int n_slabs, nts_vid_t feature_size, void *stream);
+float nts_gather_plan_tuned_ms(const nts_gather_plan *plan); /* time of the winning candidate of a measured plan */
 int nts_gather_plan_destroy(nts_gather_plan *plan);
 int nts_gather_plan_slabs(const nts_gather_plan *plan);
 uint64_t nts_gather_plan_bytes(const nts_gather_plan *plan);

@@ -71,6 +71,15 @@ struct nts_exchange {
   std::vector<cudaEvent_t> ev_peer;   // backward: partial of chunk i finished
   // preprocessed aggregation per chunk direction (created on first use; nullptr = plain kernel)
   std::vector<std::vector<std::pair<int, nts_gather_plan *>>> plan_fwd, plan_bwd; // [P] -> (feature width, plan)
+  // receive-side strategy per (direction, width), decided once from measured launch times (decide_mode):
+  // 1 = pipeline (one launch per source partition as its rows land), 2 = merged (one launch over all remote chunks)
+  struct Mode {
+    int F, mode;
+    nts_gather_plan *merged;
+    float pipeline_ms, merged_ms; // the two estimates the decision was taken on
+  };
+  std::vector<Mode> mode_fwd, mode_bwd;
+  int forced_mode = 0;                // NTS_EXCHANGE_MODE=pipeline|merged
   uint64_t plan_min_edges = 1u << 20;
   unsigned long long timeout_ns = 30ull * 1000000000ull;
   int push_ctas = 0;
@@ -361,6 +370,125 @@ static int aggregate_chunk(nts_exchange *ex, int i, bool forward, const float *i
   return nts_segment_gather_sum(in, out, w, idx, off, base, n_rows, c.edges, F, st);
 }
 
+// min of 2 timed launches after 1 warm one (CUDA events on st; synchronises)
+template <class Fn> static int time_launches(Fn run, cudaStream_t st, float *ms) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  NTS_CUDA_OK(cudaEventCreate(&e0));
+  NTS_CUDA_OK(cudaEventCreate(&e1));
+  *ms = 1e30f;
+  int rc = 0;
+  for (int it = 0; it < 3 && !rc; it++) {
+    float t = 0.f;
+    if (cudaEventRecord(e0, st) != cudaSuccess || (rc = run()) != 0 || cudaEventRecord(e1, st) != cudaSuccess ||
+        cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&t, e0, e1) != cudaSuccess) {
+      rc = rc ? rc : -1;
+      break;
+    }
+    if (it > 0 && t < *ms)
+      *ms = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+// Pipeline or merged?  One launch per source partition hides the transfer behind the earlier chunks, but small
+// launches run at a fraction of the large-launch rate (config B at 8 GPUs: 1.8 M-edge chunks take 2x their share);
+// one merged launch is efficient but can only start when ALL rows have landed.  Decided once per (direction, width)
+// from MEASURED launch times on scratch inputs (L = local chunk, c_i = remote chunks, M = merged launch) and the
+// transfer time T of the bytes this rank receives (forward) / sends (backward) at 600 GB/s:
+//   forward : pipeline ~ L + max(sum c_i, T - L)        merged ~ max(L, T) + M
+//   backward: pipeline ~ sum c_i + max(L, T / (P-1))    merged ~ M + max(L, T)
+// Each rank decides for itself (it only changes how a rank consumes its own window / fills its own staging).
+static int decide_mode(nts_exchange *ex, bool forward, uint32_t F, cudaStream_t st, nts_exchange::Mode **out) {
+  std::vector<nts_exchange::Mode> &modes = forward ? ex->mode_fwd : ex->mode_bwd;
+  for (auto &m : modes)
+    if (m.F == (int)F) {
+      *out = &m;
+      return 0;
+    }
+  modes.push_back({(int)F, 1, nullptr, 0.f, 0.f});
+  nts_exchange::Mode &m = modes.back();
+  *out = &m;
+  const int P = ex->P, p = ex->p;
+  const uint32_t Vp = ex->d.owned_vertices;
+  uint64_t remote_edges = 0;
+  int n_remote = 0;
+  for (int i = 0; i < P; i++)
+    if (i != p && ex->chunks[i].edges && ex->need_count[i]) {
+      remote_edges += ex->chunks[i].edges;
+      n_remote++;
+    }
+  if (ex->forced_mode == 1 || n_remote < 2 || !Vp || !ex->recv_total)
+    return 0; // nothing to merge (or pipeline forced)
+  // merged plan over all remote chunks (slab count measured)
+  std::vector<nts_plan_part> parts;
+  for (int i = 0; i < P; i++) {
+    if (i == p || !ex->chunks[i].edges || !ex->need_count[i])
+      continue;
+    const nts_exchange_chunk &c = ex->chunks[i];
+    nts_plan_part pt = {};
+    if (forward) {
+      pt.offsets = c.column_offset, pt.indices = c.slots, pt.weight = c.weight_forward;
+      pt.index_base = 0, pt.index_add = ex->recv_offs[i], pt.n_rows = Vp, pt.row_add = 0;
+    } else {
+      pt.offsets = c.row_offset_compact, pt.indices = c.column_indices, pt.weight = c.weight_backward;
+      pt.index_base = ex->d.dst_start, pt.index_add = 0, pt.n_rows = ex->need_count[i], pt.row_add = ex->recv_offs[i];
+    }
+    pt.n_edges = c.edges;
+    parts.push_back(pt);
+  }
+  const uint32_t out_rows = forward ? Vp : ex->recv_total, in_rows = forward ? ex->recv_total : Vp;
+  m.merged = nts_gather_plan_create_parts(parts.data(), (int)parts.size(), out_rows, in_rows, 0, F, st);
+  if (!m.merged)
+    return -1;
+  if (ex->forced_mode == 2) {
+    m.mode = 2;
+    return 0;
+  }
+  // measure: scratch inputs (zeros: the access pattern does not depend on the values)
+  const size_t rows_max = std::max<size_t>(ex->recv_total, Vp);
+  float *a = nullptr, *b = nullptr;
+  NTS_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&a), rows_max * F * sizeof(float)));
+  if (cudaMalloc(reinterpret_cast<void **>(&b), rows_max * F * sizeof(float)) != cudaSuccess) {
+    cudaFree(a);
+    return fail(-1, "scratch allocation for the exchange mode measurement failed", __FILE__, __LINE__);
+  }
+  cudaMemsetAsync(a, 0, rows_max * F * sizeof(float), st);
+  cudaMemsetAsync(b, 0, rows_max * F * sizeof(float), st);
+  float L = 0.f, M = 0.f, sum_c = 0.f;
+  int rc = time_launches([&]() { return aggregate_chunk(ex, p, forward, a, b, F, st); }, st, &L);
+  if (!rc)
+    rc = time_launches([&]() { return nts_gather_plan_run(m.merged, a, b, F, st); }, st, &M);
+  for (int i = 0; i < P && !rc; i++) {
+    if (i == p || !ex->chunks[i].edges || !ex->need_count[i])
+      continue;
+    float c = 0.f;
+    rc = time_launches([&]() { return aggregate_chunk(ex, i, forward, a, b, F, st); }, st, &c);
+    sum_c += c;
+  }
+  cudaFree(a);
+  cudaFree(b);
+  if (rc)
+    return rc;
+  if (!ex->chunks[p].edges)
+    L = 0.f;
+  const float T = (float)((double)(forward ? ex->recv_total : ex->recv_total) * F * 4.0 / 600e9 * 1e3); // ms
+  if (forward) {
+    m.pipeline_ms = L + std::max(sum_c, T - L);
+    m.merged_ms = std::max(L, T) + M;
+  } else {
+    m.pipeline_ms = sum_c + std::max(L, T / (float)(P - 1));
+    m.merged_ms = M + std::max(L, T);
+  }
+  m.mode = m.merged_ms < m.pipeline_ms ? 2 : 1;
+  if (m.mode == 1) { // the merged plan is not needed: release its arrays
+    nts_gather_plan_destroy(m.merged);
+    m.merged = nullptr;
+  }
+  return 0;
+}
+
 extern "C" {
 
 nts_exchange *nts_exchange_create(const nts_exchange_desc *desc) {
@@ -429,6 +557,8 @@ nts_exchange *nts_exchange_create(const nts_exchange_desc *desc) {
     if (ms > 0)
       ex->timeout_ns = (unsigned long long)ms * 1000000ull;
   }
+  if (const char *t = getenv("NTS_EXCHANGE_MODE"))
+    ex->forced_mode = !strcmp(t, "pipeline") ? 1 : (!strcmp(t, "merged") ? 2 : 0);
   if (const char *t = getenv("NTS_EXCHANGE_PLAN_MIN_EDGES"))
     ex->plan_min_edges = strtoull(t, nullptr, 10);
   ex->push_ctas = std::max(8, sm_count() / 2); // enough memory-level parallelism for NVLink, half of the SMs at most
@@ -496,6 +626,9 @@ int nts_exchange_destroy(nts_exchange *ex) {
           freed.push_back(e.second);
         }
     }
+  for (auto *side : {&ex->mode_fwd, &ex->mode_bwd})
+    for (auto &m : *side)
+      nts_gather_plan_destroy(m.merged);
   cudaFree(ex->window);
   cudaFree(ex->flags);
   cudaFree(ex->tickets);
@@ -616,20 +749,41 @@ static int forward_impl(nts_exchange *ex, const float *x, float *y, nts_vid_t F,
   NTS_TRY(push_my_rows(ex, x, F, buf, epoch, wait_epoch));
   if (tr)
     NTS_CUDA_OK(cudaEventRecord(ex->tev[2], ex->comm));
-  // ---- main stream: local chunk, then the remote chunks as their rows arrive
+  // ---- main stream: local chunk, then the remote chunks - one launch per partition as its rows arrive (pipeline) or
+  // one launch over all of them once everything has landed (merged); measured once per width, see decide_mode
+  nts_exchange::Mode *mode = nullptr;
+  NTS_TRY(decide_mode(ex, true, F, st, &mode));
   NTS_TRY(aggregate_chunk(ex, p, true, x, y, F, st));
   if (tr)
     NTS_CUDA_OK(cudaEventRecord(ex->tev[3], st));
-  for (int s = 1; s < P; s++) {
-    const int i = (p + s) % P;
-    wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, 1u << i, epoch, ex->timeout_ns, ex->err_dev);
+  if (mode->mode == 2) {
+    uint32_t mask = 0;
+    for (int j = 0; j < P; j++)
+      if (j != p)
+        mask |= 1u << j;
+    wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, mask, epoch, ex->timeout_ns, ex->err_dev);
     NTS_LAUNCH_CHECK();
     if (tr)
-      NTS_CUDA_OK(cudaEventRecord(ex->tev[4 + 2 * (s - 1)], st));
-    if (ex->need_count[i])
-      NTS_TRY(aggregate_chunk(ex, i, true, ex->window + buf + (size_t)ex->recv_offs[i] * F, y, F, st));
+      NTS_CUDA_OK(cudaEventRecord(ex->tev[4], st));
+    NTS_TRY(nts_gather_plan_run(mode->merged, ex->window + buf, y, F, st));
     if (tr)
-      NTS_CUDA_OK(cudaEventRecord(ex->tev[5 + 2 * (s - 1)], st));
+      for (int s = 1; s < P; s++) { // the merged launch is reported under ring step 1, the other steps read 0
+        NTS_CUDA_OK(cudaEventRecord(ex->tev[5 + 2 * (s - 1)], st));
+        if (s + 1 < P)
+          NTS_CUDA_OK(cudaEventRecord(ex->tev[4 + 2 * s], st));
+      }
+  } else {
+    for (int s = 1; s < P; s++) {
+      const int i = (p + s) % P;
+      wait_pushed_kernel<<<1, 32, 0, st>>>(ex->flags, 1u << i, epoch, ex->timeout_ns, ex->err_dev);
+      NTS_LAUNCH_CHECK();
+      if (tr)
+        NTS_CUDA_OK(cudaEventRecord(ex->tev[4 + 2 * (s - 1)], st));
+      if (ex->need_count[i])
+        NTS_TRY(aggregate_chunk(ex, i, true, ex->window + buf + (size_t)ex->recv_offs[i] * F, y, F, st));
+      if (tr)
+        NTS_CUDA_OK(cudaEventRecord(ex->tev[5 + 2 * (s - 1)], st));
+    }
   }
   signal_consumed_kernel<<<1, 32, 0, st>>>(ex->d_peer_flags, P, p, epoch);
   NTS_LAUNCH_CHECK();
@@ -655,16 +809,32 @@ static int backward_impl(nts_exchange *ex, const float *g, float *dx, nts_vid_t 
   NTS_TRY(grow(&ex->bsend, &ex->bsend_cap, (size_t)(ex->recv_total ? ex->recv_total : 1) * F));
   if (ex->recv_total)
     NTS_CUDA_OK(cudaMemsetAsync(ex->bsend, 0, (size_t)ex->recv_total * F * sizeof(float), st));
-  // ---- per remote chunk (p+1, p+2, ...): partial gradients of its active sources -> pushed to the owner at once
-  for (int s = 1; s < P; s++) {
-    const int i = (p + s) % P;
-    float *slice = ex->bsend + (size_t)ex->recv_offs[i] * F;
-    if (ex->need_count[i])
-      NTS_TRY(aggregate_chunk(ex, i, false, g, slice, F, st));
-    NTS_CUDA_OK(cudaEventRecord(ex->ev_peer[i], st));
-    NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_peer[i], 0));
-    NTS_TRY(dma_push(ex, i, ex->bsend + (size_t)ex->recv_offs[i] * F, ex->bwd_push_off[i], ex->need_count[i], F, buf,
-                     epoch, wait_epoch, ex->comm));
+  nts_exchange::Mode *mode = nullptr;
+  NTS_TRY(decide_mode(ex, false, F, st, &mode));
+  if (mode->mode == 2) {
+    // ---- merged: ONE launch computes the partial gradients of the active sources of all remote chunks, then every
+    // slice goes to its owner through the copy engines
+    NTS_TRY(nts_gather_plan_run(mode->merged, g, ex->bsend, F, st));
+    NTS_CUDA_OK(cudaEventRecord(ex->ev_peer[p], st));
+    NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_peer[p], 0));
+    for (int s = 1; s < P; s++) {
+      const int i = (p + s) % P;
+      NTS_TRY(dma_push(ex, i, ex->bsend + (size_t)ex->recv_offs[i] * F, ex->bwd_push_off[i], ex->need_count[i], F, buf,
+                       epoch, wait_epoch, ex->comm));
+    }
+  } else {
+    // ---- pipeline: per remote chunk (p+1, p+2, ...) the partial gradients of its active sources, pushed to the
+    // owner while the next chunk computes
+    for (int s = 1; s < P; s++) {
+      const int i = (p + s) % P;
+      float *slice = ex->bsend + (size_t)ex->recv_offs[i] * F;
+      if (ex->need_count[i])
+        NTS_TRY(aggregate_chunk(ex, i, false, g, slice, F, st));
+      NTS_CUDA_OK(cudaEventRecord(ex->ev_peer[i], st));
+      NTS_CUDA_OK(cudaStreamWaitEvent(ex->comm, ex->ev_peer[i], 0));
+      NTS_TRY(dma_push(ex, i, ex->bsend + (size_t)ex->recv_offs[i] * F, ex->bwd_push_off[i], ex->need_count[i], F, buf,
+                       epoch, wait_epoch, ex->comm));
+    }
   }
   // ---- local chunk overlaps with the pushes; then everything the peers computed for my rows
   NTS_TRY(aggregate_chunk(ex, p, false, g, dx, F, st));

@@ -94,6 +94,32 @@ __global__ void plan_pairs_kernel(const uint32_t *__restrict__ perm, const uint3
   }
 }
 
+// Multi-part variants (several chunks merged into one plan): part-local row r -> output row row_add + r, mapped index
+// g -> index_add + g; edge e of the part is global edge e_off + e.
+__global__ void plan_part_keys_kernel(const uint32_t *__restrict__ off, const uint32_t *__restrict__ idx,
+                                      const uint32_t *__restrict__ slot_of, const float *__restrict__ w, uint32_t base,
+                                      uint32_t index_add, uint32_t n_rows_part, uint32_t row_add, uint32_t n_edges,
+                                      uint32_t e_off, uint32_t n_rows_total, uint32_t slab_rows, uint32_t slabs,
+                                      uint32_t *__restrict__ key, uint32_t *__restrict__ val,
+                                      uint2 *__restrict__ unsorted) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = plan_find_row(off, n_rows_part, (uint32_t)e) + row_add;
+    const uint32_t id = __ldg(idx + e);
+    const uint32_t g = (slot_of ? __ldg(slot_of + id) : id - base) + index_add;
+    uint32_t s = g / slab_rows;
+    if (s >= slabs)
+      s = slabs - 1;
+    key[e_off + e] = s * n_rows_total + r;
+    val[e_off + e] = e_off + (uint32_t)e;
+    unsorted[e_off + e] = make_uint2(g, __float_as_uint(w ? __ldg(w + e) : 1.f));
+  }
+}
+__global__ void plan_permute_pairs_kernel(const uint32_t *__restrict__ perm, const uint2 *__restrict__ unsorted,
+                                          uint32_t n_edges, uint2 *__restrict__ pairs) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges; i += (uint64_t)gridDim.x * blockDim.x)
+    pairs[i] = unsorted[__ldg(perm + i)];
+}
+
 // voff[k] = number of sorted keys < k, k in [0, n_keys]
 __global__ void plan_offsets_kernel(const uint32_t *__restrict__ sorted_key, uint32_t n_edges, uint32_t n_keys,
                                     uint32_t *__restrict__ voff) {
@@ -785,6 +811,167 @@ nts_gather_plan *nts_gather_plan_create(const nts_vid_t *offsets, const nts_vid_
   }
   return pl;
 }
+
+// Several chunks merged into ONE plan (the exchange engine aggregates all remote chunks of a rank in one launch when
+// their rows arrive faster than one chunk computes): a stable sort of all parts' edges by (slab, output row); inside a
+// segment the parts follow each other in the order given, each keeping its own edge order.
+static nts_gather_plan *build_plan_parts(const nts_plan_part *parts, int n_parts, nts_vid_t n_rows, nts_vid_t gather_rows,
+                                         int n_slabs, cudaStream_t st) {
+  auto bad = [](const char *m) -> nts_gather_plan * {
+    fail(-1, m, __FILE__, __LINE__);
+    return nullptr;
+  };
+  uint64_t total = 0;
+  for (int k = 0; k < n_parts; k++) {
+    if (parts[k].n_edges && !(parts[k].offsets && parts[k].indices))
+      return bad("null graph array in a plan part");
+    if ((uint64_t)parts[k].row_add + parts[k].n_rows > n_rows)
+      return bad("plan part rows exceed the output rows");
+    total += parts[k].n_edges;
+  }
+  if (total >= 0xffffffffull)
+    return bad("merged edge count must fit uint32 offsets");
+  if (n_slabs < 1 || gather_rows == 0)
+    n_slabs = 1;
+  if ((uint64_t)n_slabs * n_rows >= 0xffffffffull)
+    return bad("slabs * rows must fit 32-bit segment keys");
+  nts_gather_plan *pl = new nts_gather_plan();
+  pl->n_rows = n_rows;
+  pl->n_edges = total;
+  pl->gather_rows = gather_rows;
+  pl->slabs = n_slabs;
+  pl->slab_rows = gather_rows ? (gather_rows + n_slabs - 1) / n_slabs : 1;
+  pl->slab_edge.assign(n_slabs + 1, 0);
+  if (n_rows == 0 || total == 0)
+    return pl;
+  const uint32_t E = (uint32_t)total, n_keys = (uint32_t)n_slabs * n_rows;
+  uint32_t *key_in = nullptr, *key_out = nullptr, *val_in = nullptr, *val_out = nullptr;
+  uint2 *unsorted = nullptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < (uint64_t)n_keys)
+    bits++;
+  bool ok = cudaMalloc(reinterpret_cast<void **>(&pl->pairs), (size_t)E * sizeof(uint2)) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&pl->voff), ((size_t)n_keys + 1) * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&unsorted), (size_t)E * sizeof(uint2)) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&key_in), (size_t)E * 4) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&key_out), (size_t)E * 4) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&val_in), (size_t)E * 4) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&val_out), (size_t)E * 4) == cudaSuccess &&
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, val_in, val_out, (int64_t)E, 0, bits, st) ==
+                cudaSuccess &&
+            cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16) == cudaSuccess;
+  uint32_t e_off = 0;
+  for (int k = 0; k < n_parts && ok; k++) {
+    const nts_plan_part &pt = parts[k];
+    if (!pt.n_edges)
+      continue;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((pt.n_edges + 255) / 256, (uint64_t)sm_count() * 32);
+    plan_part_keys_kernel<<<blocks, 256, 0, st>>>(pt.offsets, pt.indices, pt.slot_of, pt.weight, pt.index_base,
+                                                  pt.index_add, pt.n_rows, pt.row_add, (uint32_t)pt.n_edges, e_off, n_rows,
+                                                  pl->slab_rows, (uint32_t)n_slabs, key_in, val_in, unsorted);
+    count_launch();
+    e_off += (uint32_t)pt.n_edges;
+  }
+  if (ok)
+    ok = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, val_in, val_out, (int64_t)E, 0, bits, st) ==
+         cudaSuccess;
+  if (ok) {
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)E + 255) / 256, (uint64_t)sm_count() * 32);
+    plan_permute_pairs_kernel<<<blocks, 256, 0, st>>>(val_out, unsorted, E, pl->pairs);
+    count_launch();
+    const unsigned kb = (unsigned)std::min<uint64_t>(((uint64_t)n_keys + 256) / 256, (uint64_t)sm_count() * 32);
+    plan_offsets_kernel<<<kb, 256, 0, st>>>(key_out, E, n_keys, pl->voff);
+    count_launch();
+    std::vector<uint32_t> h(n_slabs + 1);
+    ok = cudaStreamSynchronize(st) == cudaSuccess;
+    for (int s = 0; s <= n_slabs && ok; s++)
+      ok = cudaMemcpy(&h[s], pl->voff + (size_t)s * n_rows, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    for (int s = 0; s <= n_slabs; s++)
+      pl->slab_edge[s] = h[s];
+  }
+  if (ok)
+    ok = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+  cudaFree(key_in), cudaFree(key_out), cudaFree(val_in), cudaFree(val_out), cudaFree(tmp), cudaFree(unsorted);
+  if (!ok) {
+    fail(-1, "nts_gather_plan_create_parts: device allocation or preprocessing failed", __FILE__, __LINE__);
+    cudaFree(pl->pairs), cudaFree(pl->voff);
+    delete pl;
+    return nullptr;
+  }
+  return pl;
+}
+
+// n_slabs >= 1: that slab count; n_slabs == 0: measured for feature_size like nts_gather_plan_create_tuned
+nts_gather_plan *nts_gather_plan_create_parts(const nts_plan_part *parts, int n_parts, nts_vid_t n_rows,
+                                              nts_vid_t gather_rows, int n_slabs, nts_vid_t feature_size, void *stream) {
+  if (!parts || n_parts < 1) {
+    fail(-1, "no plan parts", __FILE__, __LINE__);
+    return nullptr;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (n_slabs >= 1)
+    return build_plan_parts(parts, n_parts, n_rows, gather_rows, n_slabs, st);
+  uint64_t total = 0;
+  for (int k = 0; k < n_parts; k++)
+    total += parts[k].n_edges;
+  const int s_max = nts_gather_plan_pick_slabs(gather_rows, total, n_rows, feature_size, 16ull << 20);
+  nts_gather_plan *best = build_plan_parts(parts, n_parts, n_rows, gather_rows, 1, st);
+  if (!best || s_max <= 1 || total == 0 || feature_size == 0)
+    return best;
+  float *x = nullptr, *y = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const size_t xb = (size_t)gather_rows * feature_size * sizeof(float), yb = (size_t)n_rows * feature_size * sizeof(float);
+  bool ok = cudaMalloc(reinterpret_cast<void **>(&x), xb) == cudaSuccess &&
+            cudaMalloc(reinterpret_cast<void **>(&y), yb) == cudaSuccess &&
+            cudaMemsetAsync(x, 0, xb, st) == cudaSuccess && cudaMemsetAsync(y, 0, yb, st) == cudaSuccess &&
+            cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+  auto time_plan = [&](nts_gather_plan *pl, float *ms) -> bool {
+    *ms = 1e30f;
+    for (int it = 0; it < 3; it++) {
+      float t = 0.f;
+      if (cudaEventRecord(e0, st) != cudaSuccess || run_plan(pl, x, y, feature_size, st) != 0 ||
+          cudaEventRecord(e1, st) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess ||
+          cudaEventElapsedTime(&t, e0, e1) != cudaSuccess)
+        return false;
+      if (it > 0 && t < *ms)
+        *ms = t;
+    }
+    return true;
+  };
+  float best_ms = 0.f;
+  ok = ok && time_plan(best, &best_ms);
+  for (int s = 2; ok; s *= 2) {
+    const int cand = s > s_max ? s_max : s;
+    nts_gather_plan *pl = build_plan_parts(parts, n_parts, n_rows, gather_rows, cand, st);
+    float ms = 0.f;
+    if (!pl || !time_plan(pl, &ms)) {
+      nts_gather_plan_destroy(pl);
+      break;
+    }
+    if (ms < best_ms) {
+      nts_gather_plan_destroy(best);
+      best = pl;
+      best_ms = ms;
+    } else {
+      nts_gather_plan_destroy(pl);
+      if (ms > 1.1f * best_ms)
+        break;
+    }
+    if (cand == s_max)
+      break;
+  }
+  cudaFree(x), cudaFree(y);
+  if (e0)
+    cudaEventDestroy(e0);
+  if (e1)
+    cudaEventDestroy(e1);
+  best->tuned_ms = best_ms;
+  return best;
+}
+
+float nts_gather_plan_tuned_ms(const nts_gather_plan *pl) { return pl ? pl->tuned_ms : 0.f; }
 
 // Slab count by measurement.  Whether bucketing pays depends on how skewed the gathered rows are (hub sources stay in
 // L1/L2 by themselves: on the Zipf graph of config B one launch at F=602 takes 12.8 ms unbucketed, 20.9 ms with 14
