@@ -10,5 +10,5 @@ timeout 900 ncu --set full --clock-control none --kernel-name-base demangled \
 timeout 900 ncu --set full --clock-control none --kernel-name-base demangled \
     -k 'regex:planned_gather_sum_kernel<\(int\)5' -s 60 -c 8 -o $O/prof_r2_plan_F602_uniform $B --zipf-s 0 > $O/ncu_full_F602_uniform.log 2>&1
 grep -h "No kernels\|Report" $O/ncu_full_F602.log $O/ncu_full_F128.log $O/ncu_full_F602_uniform.log
-python bench.py --toolkit gat --steps 5 --warmup 3 > $O/bench_r2_gat_b.json 2> $O/bench_r2_gat_b.err
+python bench.py --toolkit gat --steps 5 --warmup 3 --no-e2e > $O/bench_r2_gat_b.json 2> $O/bench_r2_gat_b.err
 head -c 300 $O/bench_r2_gat_b.json; tail -n 2 $O/bench_r2_gat_b.err
