@@ -470,6 +470,18 @@ int nts_host_mirror_index(const nts_vid_t *edges_src_dst, uint64_t n_edges, nts_
                           const nts_vid_t *partition_offset, int rank, nts_vid_t *mirror_index,
                           nts_vid_t *owned);
 
+/* ---- feature / label / mask tables (GNNDatum, core/ntsDataloador.hpp) ----------------------------------------------------
+ * Text tables exactly as GNNDatum::readFeature_Label_Mask (:156-221) reads them - "id f0 .. fF-1", "id label",
+ * "id train|val|eval|test", the k-th label / mask record belongs to the k-th feature record - parsed in parallel;
+ * rows with id in [v_begin, v_end) land at id - v_begin (mask: train 0, val/eval 1, test 2, other 3).  label_path /
+ * mask_path (and their outputs) may be NULL.  Returns 0, or a negative code (-2/-3/-4 unreadable file, -5 malformed). */
+int nts_host_read_feature_label_mask(const char *feature_path, const char *label_path, const char *mask_path,
+                                     nts_vid_t feature_size, nts_vid_t v_begin, nts_vid_t v_end, float *features,
+                                     int64_t *labels, int32_t *masks);
+/* rows [v_begin, v_end) of a packed float32 [V, feature_size] table (the twin of the packed binary edge file) */
+int nts_host_read_feature_binary(const char *path, nts_vid_t feature_size, nts_vid_t v_begin, nts_vid_t v_end,
+                                 float *features);
+
 #ifdef __cplusplus
 }
 #endif

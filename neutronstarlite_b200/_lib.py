@@ -95,6 +95,8 @@ SIGNATURES = {
     "nts_host_chunk_edge_counts": (_int, [_vp, _u64, _vp, _int, _int, _vp]),
     "nts_host_build_chunk": (_int, [_vp, _u64, _u32, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nts_host_mirror_index": (_int, [_vp, _u64, _u32, _vp, _int, _vp, _vp]),
+    "nts_host_read_feature_label_mask": (_int, [C.c_char_p, C.c_char_p, C.c_char_p, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "nts_host_read_feature_binary": (_int, [C.c_char_p, _u32, _u32, _u32, _vp]),
 }
 
 

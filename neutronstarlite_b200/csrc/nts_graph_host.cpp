@@ -209,3 +209,142 @@ int nts_host_mirror_index(const nts_vid_t *edges, uint64_t n_edges, nts_vid_t V,
 }
 
 } // extern "C"
+
+// ---- feature / label / mask tables --------------------------------------------------------------------
+// GNNDatum::readFeature_Label_Mask (core/ntsDataloador.hpp:156-221) reads three text tables with one istream each,
+// record by record: "id f0 .. fF-1", "id label", "id train|val|eval|test"; the k-th record of the label and mask
+// tables belongs to the k-th record of the feature table (they are consumed in lock step, whatever their id column
+// says), rows whose id lies in [v_begin, v_end) land at id - v_begin.  Same contract here, but the files are read
+// whole and the records parsed in parallel (strtof: correctly rounded like the istream extraction).  A packed binary
+// table (float32 [V, F] row-major, the twin of the reference's packed binary edge file) is read with one pread of the
+// owned rows.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+namespace {
+
+bool slurp(const char *path, std::string *out) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0)
+    return false;
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return false;
+  }
+  out->resize((size_t)st.st_size);
+  size_t done = 0;
+  while (done < out->size()) {
+    ssize_t n = pread(fd, &(*out)[done], out->size() - done, (off_t)done);
+    if (n <= 0)
+      break;
+    done += (size_t)n;
+  }
+  close(fd);
+  return done == out->size();
+}
+
+// start offset of every non-empty line
+std::vector<size_t> line_starts(const std::string &s) {
+  std::vector<size_t> v;
+  size_t i = 0, n = s.size();
+  while (i < n) {
+    while (i < n && (s[i] == '\n' || s[i] == '\r' || s[i] == ' ' || s[i] == '\t'))
+      i++;
+    if (i >= n)
+      break;
+    v.push_back(i);
+    while (i < n && s[i] != '\n')
+      i++;
+  }
+  return v;
+}
+
+} // namespace
+
+extern "C" {
+
+int nts_host_read_feature_label_mask(const char *feature_path, const char *label_path, const char *mask_path,
+                                     nts_vid_t feature_size, nts_vid_t v_begin, nts_vid_t v_end, float *features,
+                                     int64_t *labels, int32_t *masks) {
+  if (!feature_path || !features || v_end < v_begin)
+    return -1;
+  std::string ftr, lbl, msk;
+  if (!slurp(feature_path, &ftr))
+    return -2;
+  if (label_path && labels && !slurp(label_path, &lbl))
+    return -3;
+  if (mask_path && masks && !slurp(mask_path, &msk))
+    return -4;
+  const std::vector<size_t> fl = line_starts(ftr), ll = line_starts(lbl), ml = line_starts(msk);
+  const int64_t n = (int64_t)fl.size();
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(| : bad)
+  for (int64_t k = 0; k < n; k++) {
+    const char *p = ftr.c_str() + fl[k];
+    char *end = nullptr;
+    const unsigned long id = strtoul(p, &end, 10);
+    if (end == p) {
+      bad |= 1;
+      continue;
+    }
+    if (id < v_begin || id >= v_end)
+      continue;
+    float *row = features + (size_t)(id - v_begin) * feature_size;
+    p = end;
+    for (nts_vid_t f = 0; f < feature_size; f++) {
+      row[f] = strtof(p, &end);
+      if (end == p)
+        bad |= 2; // fewer than feature_size values on the line
+      p = end;
+    }
+    if (labels && (size_t)k < ll.size()) {
+      const char *q = lbl.c_str() + ll[k];
+      strtoul(q, &end, 10); // the id column is read and ignored, like the reference's `input_lbl >> la`
+      labels[id - v_begin] = strtol(end, nullptr, 10);
+    }
+    if (masks && (size_t)k < ml.size()) {
+      const char *q = msk.c_str() + ml[k];
+      strtoul(q, &end, 10);
+      while (*end == ' ' || *end == '\t')
+        end++;
+      int m = 3; // core/ntsDataloador.hpp:196-205
+      if (!strncmp(end, "train", 5))
+        m = 0;
+      else if (!strncmp(end, "eval", 4) || !strncmp(end, "val", 3))
+        m = 1;
+      else if (!strncmp(end, "test", 4))
+        m = 2;
+      masks[id - v_begin] = m;
+    }
+  }
+  return bad ? -5 : 0;
+}
+
+// rows [v_begin, v_end) of a packed float32 [V, feature_size] table
+int nts_host_read_feature_binary(const char *path, nts_vid_t feature_size, nts_vid_t v_begin, nts_vid_t v_end,
+                                 float *features) {
+  if (!path || !features || v_end < v_begin)
+    return -1;
+  int fd = open(path, O_RDONLY);
+  if (fd < 0)
+    return -2;
+  const size_t row = (size_t)feature_size * sizeof(float);
+  size_t want = (size_t)(v_end - v_begin) * row, done = 0;
+  const off_t base = (off_t)((size_t)v_begin * row);
+  char *dst = reinterpret_cast<char *>(features);
+  while (done < want) {
+    ssize_t n = pread(fd, dst + done, want - done, base + (off_t)done);
+    if (n <= 0)
+      break;
+    done += (size_t)n;
+  }
+  close(fd);
+  return done == want ? 0 : -3;
+}
+
+} // extern "C"
