@@ -2,18 +2,24 @@
 """bench.py - the headline benchmark of BASELINE.json: GCN epochs/s and aggregated-edges/s on the Reddit-shaped
 synthetic graph (232 965 V, 114.6 M power-law edges + self loops, LAYERS 602-128-41, fp32), N GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit|products|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload reddit|products|papers100m|tiny] [--toolkit gcn|gcn_eager|gat]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1: one rank per GPU, NCCL)
 
-One step = one GCN training epoch through the reference-shaped API (toolkits.GCNImpl <-> toolkits/GCN.hpp):
-3 aggregation calls (fwd 602, fwd 128, bwd 128) + the dense GEMMs, loss, tape backward, Adam (+ NCCL gradient
-all-reduce for N > 1).  N > 1 partitions the SAME graph with the reference's partitioner (strong scaling).
+One step = one training epoch through the reference-shaped API (toolkits.GCNImpl <-> toolkits/GCN.hpp):
+3 aggregation calls (fwd 602, fwd 128, bwd 128) + the dense GEMMs, loss, tape backward, gradient all-reduce (N > 1),
+fused Adam.  N > 1 partitions the SAME graph with the reference's partitioner (strong scaling) and exchanges rows
+through the peer-memory engine (csrc/nts_exchange.cu).  `--workload products` / `papers100m` are configs C / E,
+`--toolkit gat` is config D (3-layer 8-head GAT on the fused attention aggregation, 1 GPU).
 
 Prints ONE JSON line (rank 0).  `value` = aggregated edges per second over the whole job (3*E / epoch time) with
 inputs resident in HBM; `e2e` = the same with the feature matrix coming from pinned host memory every step and the
-loss read back; `roofline` = the layer-0 forward aggregation kernel (F=602) timed live with CUDA events;
-`cpu_baseline` / `--impl reference` = the UNMODIFIED reference CPU GCN (toolkits/GCN_CPU.hpp via oracle/_ref, built
-from /root/reference by oracle/Makefile) on a bounded edge sample of the same workload on this box's host cores.
+loss read back; `roofline` = the layer-0 forward aggregation kernel timed live with CUDA events (`frac` algorithmic
+bytes, `frac_dram` ncu DRAM bytes of the committed capture of the same kernel, `frac_min` compulsory bytes);
+`parity` (N > 1) = the benchmarked distributed operator against a float64 reference on this box; `exchange_timeline`
+(N > 1) = per-phase device time of one forward exchange; `cpu_baseline` / `--impl reference` = the UNMODIFIED
+reference CPU GCN (toolkits/GCN_CPU.hpp via oracle/_ref, built from /root/reference by oracle/Makefile) on this box's
+usable host threads - on the workload itself when it fits the time budget, else on a stated 1/div scale model.
 """
 import argparse
 import json
