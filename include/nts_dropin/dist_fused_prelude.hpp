@@ -12,3 +12,4 @@
 #undef DistGPUGetDepNbrOp
 #include "nts_dropin/core/ntsDistGPUFusedGraphOp.hpp"
 #include "nts_dropin/core/ntsDistGPUGetDepNbrOp.hpp"
+#include "nts_dropin/core/ntsDistGPUFusedGATOp.hpp"
