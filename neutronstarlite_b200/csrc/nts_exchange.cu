@@ -5,14 +5,18 @@
 // (comm/network.cpp:159-844).  Peer-memory ("p2p") transport, PUSH model, pipelined per source partition like the
 // reference's ring (aggregate chunk (p+s) while chunk (p+s+1) is in flight, core/graph.hpp:3678-3719):
 //
-//   forward   ONE persistent kernel on a high-priority side stream gathers, for every peer j in ring order
-//             (p-1, p-2, ...), the rows of X_p that j reads and STORES them straight into j's receive window over
-//             NVLink (CUDA-IPC mapping; no window copy of X, no packing pass), then raises pushed[p] in j's flags.
-//             Meanwhile the main stream aggregates the local chunk and then, for s = 1..P-1, waits for the flag of
-//             partition (p+s) and aggregates chunk (p+s) from its slice of the receive window.
-//   backward  per remote chunk (p+s): partial gradients of its active sources (compact CSR) into a local staging
-//             slice, which the side stream pushes into the owner's window as soon as that launch has finished;
-//             the local chunk overlaps with the pushes; one scatter-add of everything received.
+//   forward   send side (high-priority side streams, ring order p-1, p-2, ...): a peer that reads only some of my rows
+//             is served by the persistent gather kernel, which gathers them straight from the caller's tensor and
+//             STORES them into the peer's receive window over NVLink (CUDA-IPC mapping; no window copy of X, no
+//             packing pass); a peer that reads ALL my rows gets one contiguous copy-engine transfer (no SM time);
+//             either way pushed[p] is then raised in the peer's flags.  Receive side (main stream): the local chunk,
+//             then either one aggregation launch per source partition (p+s) as soon as ITS flag is up (pipeline), or
+//             ONE launch over all remote chunks once every flag is up (merged) - chosen once per width from measured
+//             launch times (decide_mode).
+//   backward  partial gradients of the active sources of every remote chunk (per chunk, or in one merged launch) into a
+//             local staging; the copy engines push each slice into its owner's window; the local chunk overlaps with
+//             the pushes; one scatter-add of everything received.
+//   mirrors   DistGPUGetDepNbrOp forward / backward on the same windows (nts_exchange_fetch_mirrors / return_mirror_grads).
 //
 // Cross-GPU ordering: epoch-numbered flags in peer memory, release / acquire at system scope:
 //   pushed[j]   (in my flags)  = last epoch for which rank j's rows have landed in my window,
